@@ -1,0 +1,284 @@
+"""ctypes binding of libaddapt_b200.so (include/addapt_b200.h).  Plumbing only -- no arithmetic here.
+
+Arrays may be numpy arrays (host) or anything exposing ``data_ptr()`` (torch CUDA tensors): the engine
+detects host vs device pointers itself.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+DEFAULT_PAR = os.path.join(ROOT, "params", "rna_turner2004_reconstructed.par")
+
+# the theophylline aptamer of the reference's tests (tests/test_scoring.cc:45-48)
+THEOPHYLLINE = ("GAUACCAGCCGAAAGGCCCUUGGCAGC", "(...((.(((....)))....))...)", 0.32)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Motif(C.Structure):
+    _fields_ = [("seq", C.c_char_p), ("fold", C.c_char_p), ("kd_uM", C.c_double)]
+
+
+class _Problem(C.Structure):
+    _fields_ = [("n", C.c_int), ("init_seq", C.c_char_p), ("n_macro", C.c_int), ("macro_cst", C.POINTER(C.c_char_p)),
+                ("n_terms", C.c_int), ("term_macro", C.POINTER(C.c_int)), ("term_cond", C.POINTER(C.c_int)),
+                ("term_favorable", C.POINTER(C.c_int)), ("term_weight", C.POINTER(C.c_double)), ("motif", _Motif),
+                ("n_ctx", C.c_int), ("ctx_before", C.POINTER(C.c_char_p)), ("ctx_after", C.POINTER(C.c_char_p)),
+                ("float_dg", C.c_int)]
+
+
+def _b(s):
+    return s if isinstance(s, bytes) else s.encode()
+
+
+class Problem:
+    """A design problem: ≙ Device + ScoreFunction of the reference (include/model.hh, include/scoring.hh).
+
+    seq: mixed-case sequence (upper = mutable); macrostates: {name: constraint}; terms: list of
+    (macrostate name, 'apo'|'holo', favorable bool, weight); motif: (seq, fold, kd_uM) or None;
+    contexts: list of (before, after).
+    """
+
+    def __init__(self, seq, macrostates, terms, motif=None, contexts=None, float_dg=False):
+        self.seq, self.macrostates, self.terms, self.motif = seq, dict(macrostates), list(terms), motif
+        self.contexts, self.float_dg = list(contexts or []), bool(float_dg)
+        names = list(self.macrostates)
+        k = self._keep = {}
+        k["macro"] = (C.c_char_p * max(len(names), 1))(*([_b(self.macrostates[m]) for m in names] or [b""]))
+        T = self.terms
+        k["tm"] = (C.c_int * max(len(T), 1))(*([names.index(t[0]) for t in T] or [0]))
+        k["tc"] = (C.c_int * max(len(T), 1))(*([1 if t[1] == "holo" else 0 for t in T] or [0]))
+        k["tf"] = (C.c_int * max(len(T), 1))(*([1 if t[2] else 0 for t in T] or [0]))
+        k["tw"] = (C.c_double * max(len(T), 1))(*([float(t[3]) for t in T] or [0.0]))
+        ctx = self.contexts
+        k["cb"] = (C.c_char_p * max(len(ctx), 1))(*([_b(c[0]) for c in ctx] or [b""]))
+        k["ca"] = (C.c_char_p * max(len(ctx), 1))(*([_b(c[1]) for c in ctx] or [b""]))
+        m = _Motif(_b(motif[0]), _b(motif[1]), float(motif[2])) if motif else _Motif(None, None, 0.0)
+        self.c = _Problem(len(seq), _b(seq), len(names), k["macro"], len(T), k["tm"], k["tc"], k["tf"], k["tw"], m,
+                          len(ctx), k["cb"], k["ca"], int(self.float_dg))
+        self.n = len(seq)
+        self.n_term_values = max(len(ctx), 1) * len(T)
+
+    def as_oracle_dict(self):
+        return dict(seq=self.seq, macrostates=self.macrostates, terms=self.terms, motif=self.motif, contexts=self.contexts)
+
+
+def library_path():
+    return os.path.join(HERE, "libaddapt_b200.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Load libaddapt_b200.so (built in-tree by `make` / __graft_entry__.build()).  Raises if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise EngineError("libaddapt_b200.so is not built (run `make` or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, ci, cd, cs = C.c_void_p, C.c_int, C.c_double, C.c_char_p
+    L.adp_engine_create.argtypes = [ci, cs, C.POINTER(vp)]
+    L.adp_engine_destroy.argtypes = [vp]
+    L.adp_engine_destroy.restype = None
+    L.adp_last_error.argtypes = [vp]
+    L.adp_last_error.restype = cs
+    L.adp_engine_set_stream.argtypes = [vp, vp]
+    L.adp_engine_set_async.argtypes = [vp, ci]
+    L.adp_engine_sync.argtypes = [vp]
+    L.adp_kT_kcal.argtypes = [vp]
+    L.adp_kT_kcal.restype = cd
+    L.adp_device_count.restype = ci
+    L.adp_launch_count.argtypes = [vp]
+    L.adp_launch_count.restype = C.c_uint64
+    L.adp_eval_structure.argtypes = [vp, cs, cs, C.POINTER(C.c_int32)]
+    L.adp_motif_contribution.argtypes = [vp, C.POINTER(_Motif), C.POINTER(C.c_int32)]
+    L.adp_mfe_batch.argtypes = [vp, ci, ci, vp, cs, C.POINTER(_Motif), vp, vp]
+    L.adp_pf_batch.argtypes = [vp, ci, ci, vp, cs, C.POINTER(_Motif), vp, vp]
+    L.adp_fold_eval_batch.argtypes = [vp, ci, ci, vp, C.POINTER(_Motif), ci, vp, vp, vp, vp, vp]
+    L.adp_score_batch.argtypes = [vp, C.POINTER(_Problem), ci, vp, vp, vp]
+    L.adp_mc_run.argtypes = [vp, C.POINTER(_Problem), ci, C.c_uint64, C.c_uint64, ci, ci, C.POINTER(cd), vp, vp, vp, vp, vp, vp]
+    L.adp_measure_dfma_rate.argtypes = [vp, C.POINTER(cd)]
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return C.c_void_p(a.ctypes.data)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    raise TypeError(type(a))
+
+
+def seqs_to_array(seqs):
+    """list of equal-length strings (or a (B,n) uint8 array) -> contiguous (B,n) uint8 array."""
+    if isinstance(seqs, np.ndarray):
+        return np.ascontiguousarray(seqs, dtype=np.uint8)
+    n = len(seqs[0])
+    assert all(len(s) == n for s in seqs), "all sequences of a batch must have the same length"
+    return np.frombuffer(b"".join(_b(s) for s in seqs), dtype=np.uint8).reshape(len(seqs), n).copy()
+
+
+def tri_index(n, i, j):
+    """index of pair (i,j), 0-based, in the row-major upper triangle (diagonal included) the engine writes."""
+    if i > j:
+        i, j = j, i
+    return i * n - i * (i - 1) // 2 + (j - i)
+
+
+class Engine:
+    """One engine per GPU.  Thin wrapper: every method is one C-ABI call."""
+
+    def __init__(self, device=0, par_file=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.adp_engine_create(device, _b(par_file or DEFAULT_PAR), C.byref(h))
+        if rc != 0:
+            raise EngineError("adp_engine_create failed (%d): %s" % (rc, (self.lib.adp_last_error(None) or b"").decode()))
+        self.h = h
+        self.kT = self.lib.adp_kT_kcal(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.adp_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError("engine call failed (%d): %s" % (rc, (self.lib.adp_last_error(self.h) or b"").decode()))
+
+    def _motif(self, motif):
+        if motif is None:
+            return None, None
+        m = _Motif(_b(motif[0]), _b(motif[1]), float(motif[2]))
+        return C.byref(m), m
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.adp_engine_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_async(self, flag):
+        self._check(self.lib.adp_engine_set_async(self.h, int(flag)))
+
+    def sync(self):
+        self._check(self.lib.adp_engine_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.adp_launch_count(self.h))
+
+    def dfma_rate(self):
+        r = C.c_double()
+        self._check(self.lib.adp_measure_dfma_rate(self.h, C.byref(r)))
+        return r.value
+
+    def eval_structure(self, seq, structure):
+        e = C.c_int32()
+        self._check(self.lib.adp_eval_structure(self.h, _b(seq), _b(structure), C.byref(e)))
+        return e.value
+
+    def motif_contribution(self, motif):
+        ref, keep = self._motif(motif)
+        c = C.c_int32()
+        self._check(self.lib.adp_motif_contribution(self.h, ref, C.byref(c)))
+        return c.value
+
+    # ---- batched folds (host numpy in / out) ------------------------------------------------
+    def mfe(self, seqs, cst=None, motif=None, structures=True):
+        a = seqs_to_array(seqs)
+        B, n = a.shape
+        e = np.zeros(B, dtype=np.int32)
+        st = np.zeros((B, n), dtype=np.uint8) if structures else None
+        ref, keep = self._motif(motif)
+        self._check(self.lib.adp_mfe_batch(self.h, B, n, _ptr(a), _b(cst) if cst else None, ref, _ptr(e), _ptr(st)))
+        return (e, [bytes(r).decode() for r in st]) if structures else e
+
+    def pf(self, seqs, cst=None, motif=None, bppm=False):
+        a = seqs_to_array(seqs)
+        B, n = a.shape
+        dg = np.zeros(B)
+        bp = np.zeros((B, n * (n + 1) // 2)) if bppm else None
+        ref, keep = self._motif(motif)
+        self._check(self.lib.adp_pf_batch(self.h, B, n, _ptr(a), _b(cst) if cst else None, ref, _ptr(dg), _ptr(bp)))
+        return (dg, bp) if bppm else dg
+
+    def fold_eval(self, seqs, motif, queries=(), full=False):
+        a = seqs_to_array(seqs)
+        B, n = a.shape
+        qi = np.array([q[0] for q in queries], dtype=np.int32)
+        qj = np.array([q[1] for q in queries], dtype=np.int32)
+        dg = np.zeros((B, 2))
+        pr = np.zeros((B, 2, len(queries))) if len(queries) else None
+        bp = np.zeros((B, 2, n * (n + 1) // 2)) if full else None
+        ref, keep = self._motif(motif)
+        self._check(self.lib.adp_fold_eval_batch(self.h, B, n, _ptr(a), ref, len(queries), _ptr(qi) if len(queries) else None,
+                                                 _ptr(qj) if len(queries) else None, _ptr(dg), _ptr(pr), _ptr(bp)))
+        return dg, pr, bp
+
+    def fold_eval_raw(self, B, n, seqs, motif, n_query, qi, qj, dg, probs, bppm=None):
+        """Pointer-level call for bench.py: every array may be a torch tensor (device or pinned host)."""
+        ref, keep = self._motif(motif)
+        self._check(self.lib.adp_fold_eval_batch(self.h, B, n, _ptr(seqs), ref, n_query, _ptr(qi), _ptr(qj), _ptr(dg), _ptr(probs), _ptr(bppm)))
+
+    def mfe_raw(self, B, n, seqs, e, structs=None, cst=None, motif=None):
+        ref, keep = self._motif(motif)
+        self._check(self.lib.adp_mfe_batch(self.h, B, n, _ptr(seqs), _b(cst) if cst else None, ref, _ptr(e), _ptr(structs)))
+
+    def pf_raw(self, B, n, seqs, dg, bppm=None, cst=None, motif=None):
+        ref, keep = self._motif(motif)
+        self._check(self.lib.adp_pf_batch(self.h, B, n, _ptr(seqs), _b(cst) if cst else None, ref, _ptr(dg), _ptr(bppm)))
+
+    # ---- design problem --------------------------------------------------------------------
+    def score(self, problem, seqs, want_terms=False):
+        a = seqs_to_array(seqs)
+        B, n = a.shape
+        assert n == problem.n
+        out = np.zeros(B)
+        terms = np.zeros((B, problem.n_term_values)) if want_terms else None
+        self._check(self.lib.adp_score_batch(self.h, C.byref(problem.c), B, _ptr(a), _ptr(out), _ptr(terms)))
+        return (out, terms) if want_terms else out
+
+    def score_raw(self, problem, B, seqs, score, terms=None):
+        self._check(self.lib.adp_score_batch(self.h, C.byref(problem.c), B, _ptr(seqs), _ptr(score), _ptr(terms)))
+
+    def mc_run(self, problem, n_traj, seed, n_steps, thermostat=("annealing", 5.0, 0.0, 300), traj_id0=0):
+        n = problem.n
+        if thermostat[0] == "fixed":
+            kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
+        else:
+            kind, ta = 1, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
+        fs = np.zeros((n_traj, n), dtype=np.uint8)
+        bs = np.zeros((n_traj, n), dtype=np.uint8)
+        fsc, bsc = np.zeros(n_traj), np.zeros(n_traj)
+        bst = np.zeros(n_traj, dtype=np.int32)
+        oc = np.zeros((n_traj, 4), dtype=np.uint32)
+        self._check(self.lib.adp_mc_run(self.h, C.byref(problem.c), n_traj, seed, traj_id0, n_steps, kind, ta,
+                                        _ptr(fs), _ptr(fsc), _ptr(bs), _ptr(bsc), _ptr(bst), _ptr(oc)))
+        return dict(final_seq=[bytes(r).decode() for r in fs], final_score=fsc, best_seq=[bytes(r).decode() for r in bs],
+                    best_score=bsc, best_step=bst, outcomes=oc)
+
+    def mc_run_raw(self, problem, n_traj, seed, traj_id0, n_steps, thermostat, final_seq=None, final_score=None,
+                   best_seq=None, best_score=None, best_step=None, outcomes=None):
+        if thermostat[0] == "fixed":
+            kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
+        else:
+            kind, ta = 1, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
+        self._check(self.lib.adp_mc_run(self.h, C.byref(problem.c), n_traj, seed, traj_id0, n_steps, kind, ta, _ptr(final_seq),
+                                        _ptr(final_score), _ptr(best_seq), _ptr(best_score), _ptr(best_step), _ptr(outcomes)))

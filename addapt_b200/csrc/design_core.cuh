@@ -1,0 +1,211 @@
+// Score function and Monte-Carlo step on the device, one design (trajectory) per CTA.
+//
+//   score_construct  ≙ ScoreFunction::evaluate / evaluate_terms + MacrostateProbTerm::evaluate
+//                      (reference src/scoring.cc:114-158, 233-259): for every context, the apo and holo
+//                      ensembles are filled unconstrained and under each macrostate constraint
+//                      (ViennaRnaFold::macrostate_prob, :53-71), P = exp((G_tot - G_cst)/kT), term = log P or
+//                      log(1-P), score = sum of weight * term, summed over contexts.
+//   mc_trajectory    ≙ MonteCarlo::apply (src/sampling.cc:22-107) with UnbiasedMutationMove (:287-303),
+//                      mutate_recursively (:205-282, precompiled on the host into per-position closures),
+//                      Fixed / Annealing thermostats (:305-338) and the Metropolis rule (:76-89).
+// Random numbers: Philox4x32-10, key = seed, counter = (step, 0, trajectory id lo, hi); word 0 picks the
+// position, word 1 the nucleotide, words 2-3 the 53-bit acceptance threshold.
+#pragma once
+#include "fold_jobs.cuh"
+
+namespace adp {
+
+constexpr int kMaxCtx = 8;
+constexpr int kMaxFlank = 64;
+constexpr int kMaxTerms = 16;
+constexpr int kMaxMacro = 8;
+constexpr int kMaxClosure = 16;     // positions changed together by one mutation (a base-pair chain)
+
+struct ScoreProblemDev {
+  int32_t n;                         // raw device length
+  int32_t n_ctx;                     // >= 1 (a bare device is one context with empty flanks)
+  int32_t nb[kMaxCtx], na[kMaxCtx];
+  uint8_t before[kMaxCtx][kMaxFlank], after[kMaxCtx][kMaxFlank];
+  int32_t n_macro;
+  const ConstraintDev* csts;         // [n_ctx][n_macro], already padded with '.' over the flanks
+  int32_t n_terms;
+  int32_t term_fav[kMaxTerms];
+  int32_t term_v0[kMaxTerms];        // variant index of the unconstrained fill of the term's condition
+  int32_t term_v1[kMaxTerms];        // variant index of the constrained fill
+  double term_w[kMaxTerms];
+  int32_t V;
+  VariantDev variants[kMaxVariants]; // cst_id = macrostate index or -1
+  int32_t float_dg;
+  double kT;                         // kcal/mol
+  const MotifDev* motif;
+  const PfTables* T;
+  int32_t n_max;                     // longest contextual length
+};
+
+// Mutation proposals, precompiled on the host from the macrostate brackets.
+struct MoveTableDev {
+  int32_t n_free;                            // freely mutable positions (sampling.cc:177-193)
+  int16_t free_pos[kMaxLen];
+  int8_t closure_len[kMaxLen];               // per free position: how many positions change together
+  int16_t closure_pos[kMaxLen][kMaxClosure];
+  int8_t closure_comp[kMaxLen][kMaxClosure]; // 0: gets the drawn nucleotide, 1: gets its complement
+};
+
+ADP_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+ADP_HD uint8_t complement_nt(uint8_t c) { return c == 'A' ? 'U' : c == 'U' ? 'A' : c == 'G' ? 'C' : c == 'C' ? 'G' : 0; }
+
+// products and sums that must not be contracted into an FMA, so the schedule matches a plain C evaluation
+ADP_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+ADP_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+
+ADP_HD double thermostat_T(int kind, const double* args, int step) {
+  if (kind != 1) return args[0];
+  const int cycle = (int)args[2];
+  return add_rn(mul_rn((args[1] - args[0]) / cycle, (double)(step % cycle)), args[0]);   // sampling.cc:331-338
+}
+
+// Shared-memory bytes a design CTA needs besides the fold working set.
+ADP_HD size_t design_extra_bytes(int n_max) { return 64 + (size_t)(n_max + 16) * 4 + (kMaxVariants + kMaxTerms * kMaxCtx + 8) * sizeof(double); }
+
+struct DesignScratch {
+  uint8_t* full;     // contextual sequence  [n_max+16]
+  uint8_t* cur;      // current raw sequence [n_max+16]
+  uint8_t* prop;     // proposed raw sequence
+  uint8_t* best;
+  double* dg;        // [kMaxVariants]
+  double* terms;     // [kMaxCtx*kMaxTerms]
+  double* bcast;     // [8] broadcast slots
+};
+
+ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
+  d.full = cv.take<uint8_t>(n_max + 16);
+  d.cur = cv.take<uint8_t>(n_max + 16);
+  d.prop = cv.take<uint8_t>(n_max + 16);
+  d.best = cv.take<uint8_t>(n_max + 16);
+  d.dg = cv.take<double>(kMaxVariants);
+  d.terms = cv.take<double>(kMaxCtx * kMaxTerms);
+  d.bcast = cv.take<double>(8);
+}
+
+// Score of the raw sequence `raw` (n ASCII bytes, readable by every thread).  Collective; every thread gets
+// the score.  Unweighted term values are left in d.terms[ctx*n_terms + t].
+template <class E>
+ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint8_t* raw, DesignScratch& d, void* fold_small, double* mats) {
+  double score = 0.;
+  for (int x = 0; x < sp.n_ctx; x++) {
+    const int nb = sp.nb[x], na = sp.na[x], nx = nb + sp.n + na;
+    for (int p = ex.tid(); p < nx; p += ex.nthreads())
+      d.full[p] = p < nb ? sp.before[x][p] : p < nb + sp.n ? raw[p - nb] : sp.after[x][p - nb - sp.n];
+    ex.sync();
+    for (int v = 0; v < sp.V; v++) {
+      const VariantDev var = sp.variants[v];
+      PfJob job;
+      job.seq = d.full;
+      job.n = nx;
+      job.cst = var.cst_id >= 0 ? sp.csts + (size_t)x * sp.n_macro + var.cst_id : nullptr;
+      job.motif = var.use_motif ? sp.motif : nullptr;
+      job.T = sp.T;
+      job.outside = false;
+      job.dG = d.dg + v;
+      job.bppm = nullptr;
+      job.n_query = 0;
+      job.qi = nullptr; job.qj = nullptr; job.qprobs = nullptr;
+      run_pf_job(ex, job, fold_small, mats);
+      ex.sync();
+    }
+    if (ex.tid() == 0) {
+      for (int t = 0; t < sp.n_terms; t++) {
+        double g0 = d.dg[sp.term_v0[t]], g1 = d.dg[sp.term_v1[t]];
+        if (sp.float_dg) { g0 = (double)(float)g0; g1 = (double)(float)g1; }   // vrna_pf returns float
+        double p = exp((g0 - g1) / sp.kT);
+        if (!sp.term_fav[t]) p = 1. - p;
+        d.terms[x * sp.n_terms + t] = log(p);
+      }
+    }
+    ex.sync();
+    for (int t = 0; t < sp.n_terms; t++) score = add_rn(score, mul_rn(sp.term_w[t], d.terms[x * sp.n_terms + t]));
+  }
+  return score;
+}
+
+struct McResult {
+  double final_score, best_score;
+  int32_t best_step;
+  uint32_t outcomes[4];      // REJECT, ACCEPT_WORSENED, ACCEPT_UNCHANGED, ACCEPT_IMPROVED
+};
+
+// One trajectory.  d.cur must hold the start sequence (upper case).  Collective.
+template <class E>
+ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTableDev& mv, uint64_t seed, uint64_t traj_id, int n_steps,
+                          int thermo_kind, const double* thermo_args, DesignScratch& d, void* fold_small, double* mats, McResult* res) {
+  const int n = sp.n;
+  double cur_s = score_construct(ex, sp, d.cur, d, fold_small, mats);
+  double best_s = cur_s;
+  int best_step = -1;
+  uint32_t oc0 = 0, oc1 = 0, oc2 = 0, oc3 = 0;
+  for (int p = ex.tid(); p < n; p += ex.nthreads()) d.best[p] = d.cur[p];
+  ex.sync();
+  for (int step = 0; step < n_steps && mv.n_free > 0; step++) {
+    const double T = thermostat_T(thermo_kind, thermo_args, step);
+    uint32_t r[4];
+    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, 0u, (uint32_t)traj_id, (uint32_t)(traj_id >> 32), r);
+    const int slot = (int)(((uint64_t)r[0] * (uint64_t)mv.n_free) >> 32);
+    const uint8_t nt = (uint8_t)("ACGU"[r[1] >> 30]);
+    const double u = ((double)(r[2] >> 5) * 67108864. + (double)(r[3] >> 6)) / 9007199254740992.;
+    // proposal = current with the closure of the drawn position rewritten
+    for (int p = ex.tid(); p < n; p += ex.nthreads()) d.prop[p] = d.cur[p];
+    ex.sync();
+    bool changed = false;
+    const int clen = mv.closure_len[slot];
+    const uint8_t ntc = complement_nt(nt);
+    for (int q = 0; q < clen; q++) {
+      const int pos = mv.closure_pos[slot][q];
+      const uint8_t want = mv.closure_comp[slot][q] ? ntc : nt;
+      if (d.cur[pos] != want) changed = true;
+    }
+    if (ex.tid() == 0)
+      for (int q = 0; q < clen; q++) d.prop[mv.closure_pos[slot][q]] = mv.closure_comp[slot][q] ? ntc : nt;
+    ex.sync();
+    if (!changed) { oc2++; continue; }                                         // ACCEPT_UNCHANGED: not scored
+    const double prop_s = score_construct(ex, sp, d.prop, d, fold_small, mats);
+    const double diff = prop_s - cur_s;
+    const double crit = exp(diff / T);
+    if (crit < u) { oc0++; continue; }                                         // REJECT (NaN compares false: accept)
+    if (diff > 0) oc3++; else oc1++;
+    for (int p = ex.tid(); p < n; p += ex.nthreads()) d.cur[p] = d.prop[p];
+    cur_s = prop_s;
+    if (cur_s > best_s) {
+      best_s = cur_s;
+      best_step = step;
+      for (int p = ex.tid(); p < n; p += ex.nthreads()) d.best[p] = d.prop[p];
+    }
+    ex.sync();
+  }
+  if (ex.tid() == 0) {
+    res->final_score = cur_s; res->best_score = best_s; res->best_step = best_step;
+    res->outcomes[0] = oc0; res->outcomes[1] = oc1; res->outcomes[2] = oc2; res->outcomes[3] = oc3;
+  }
+}
+
+}  // namespace adp

@@ -1,0 +1,129 @@
+// sm_100a kernels for the design loop: one candidate design (score) or one trajectory (Monte Carlo) per
+// CTA.  Sequences, scores, RNG state and acceptance never leave the GPU inside the loop.
+#include "design_kernels.h"
+
+namespace adp {
+
+extern __shared__ __align__(16) unsigned char adp_dsmem[];
+
+struct DesignSmem {
+  void* fold_small;
+  double* mats;
+  DesignScratch d;
+};
+
+template <bool kSmemMats>
+__device__ __forceinline__ DesignSmem carve_design_smem(int n_max, double* gmats, size_t gmat_stride) {
+  DesignSmem s;
+  s.fold_small = adp_dsmem;
+  size_t off = (pf_small_bytes(n_max) + 15) & ~(size_t)15;
+  Carver cv(adp_dsmem + off);
+  carve_design(cv, s.d, n_max);
+  if (kSmemMats) {
+    s.mats = cv.take<double>(0);
+  } else {
+    s.mats = gmats + (size_t)blockIdx.x * gmat_stride;
+  }
+  return s;
+}
+
+template <int G, bool kSmemMats>
+__global__ void __launch_bounds__(512) score_batch_kernel(const ScoreBatchArgs a) {
+  CtaExec<G> ex;
+  DesignSmem s = carve_design_smem<kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
+  const int n = a.sp.n, nt_terms = a.sp.n_ctx * a.sp.n_terms;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.seqs[(size_t)b * n + p];
+    __syncthreads();
+    const double sc = score_construct(ex, a.sp, s.d.cur, s.d, s.fold_small, s.mats);
+    if (threadIdx.x == 0) a.score[b] = sc;
+    if (a.terms)
+      for (int t = threadIdx.x; t < nt_terms; t += blockDim.x) a.terms[(size_t)b * nt_terms + t] = s.d.terms[t];
+    __syncthreads();
+  }
+}
+
+template <int G, bool kSmemMats>
+__global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
+  CtaExec<G> ex;
+  DesignSmem s = carve_design_smem<kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
+  __shared__ McResult res;
+  const int n = a.sp.n;
+  for (int t = blockIdx.x; t < a.n_traj; t += gridDim.x) {
+    for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.init_seq[p];
+    __syncthreads();
+    mc_trajectory(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.n_steps, a.thermo_kind, a.thermo_args, s.d, s.fold_small, s.mats, &res);
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+      if (a.final_seq) a.final_seq[(size_t)t * n + p] = s.d.cur[p];
+      if (a.best_seq) a.best_seq[(size_t)t * n + p] = s.d.best[p];
+    }
+    if (threadIdx.x == 0) {
+      if (a.final_score) a.final_score[t] = res.final_score;
+      if (a.best_score) a.best_score[t] = res.best_score;
+      if (a.best_step) a.best_step[t] = res.best_step;
+      if (a.outcomes)
+        for (int k = 0; k < 4; k++) a.outcomes[(size_t)t * 4 + k] = res.outcomes[k];
+    }
+    __syncthreads();
+  }
+}
+
+LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs) {
+  LaunchPlan p = plan_pf(d, n_max, jobs, false);
+  // same shape as an inside-only fold, plus the design scratch
+  const size_t small = ((pf_small_bytes(n_max) + 15) & ~(size_t)15) + design_extra_bytes(n_max) + 64;
+  const size_t mats = pf_matrix_doubles(n_max, false) * sizeof(double);
+  p.mats_in_smem = small + mats <= d.smem_optin;
+  p.smem_bytes = p.mats_in_smem ? small + mats : small;
+  p.gmat_stride = p.mats_in_smem ? 0 : pf_matrix_doubles(n_max, false);
+  size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);
+  size_t by_threads = 2048 / p.threads;
+  size_t occ = per_sm < by_threads ? per_sm : by_threads;
+  if (occ < 1) occ = 1;
+  long grid = (long)d.sm_count * (long)occ;
+  if (grid > jobs) grid = jobs;
+  if (grid < 1) grid = 1;
+  p.grid = (int)grid;
+  return p;
+}
+
+#define ADP_DLAUNCH(KERNEL, ARGS)                                                                         \
+  do {                                                                                                    \
+    cudaError_t e_ = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes); \
+    if (e_ != cudaSuccess) return e_;                                                                     \
+    KERNEL<<<p.grid, p.threads, p.smem_bytes, stream>>>(ARGS);                                            \
+    return cudaGetLastError();                                                                            \
+  } while (0)
+
+cudaError_t launch_score(const ScoreBatchArgs& a, const LaunchPlan& p, cudaStream_t stream) {
+  if (p.mats_in_smem) {
+    switch (p.group) {
+      case 4: ADP_DLAUNCH((score_batch_kernel<4, true>), a);
+      case 2: ADP_DLAUNCH((score_batch_kernel<2, true>), a);
+      default: ADP_DLAUNCH((score_batch_kernel<1, true>), a);
+    }
+  }
+  switch (p.group) {
+    case 4: ADP_DLAUNCH((score_batch_kernel<4, false>), a);
+    case 2: ADP_DLAUNCH((score_batch_kernel<2, false>), a);
+    default: ADP_DLAUNCH((score_batch_kernel<1, false>), a);
+  }
+}
+
+cudaError_t launch_mc(const McArgs& a, const LaunchPlan& p, cudaStream_t stream) {
+  if (p.mats_in_smem) {
+    switch (p.group) {
+      case 4: ADP_DLAUNCH((mc_kernel<4, true>), a);
+      case 2: ADP_DLAUNCH((mc_kernel<2, true>), a);
+      default: ADP_DLAUNCH((mc_kernel<1, true>), a);
+    }
+  }
+  switch (p.group) {
+    case 4: ADP_DLAUNCH((mc_kernel<4, false>), a);
+    case 2: ADP_DLAUNCH((mc_kernel<2, false>), a);
+    default: ADP_DLAUNCH((mc_kernel<1, false>), a);
+  }
+}
+
+}  // namespace adp

@@ -1,0 +1,41 @@
+// Launch interface of the design kernels (score function, Monte-Carlo trajectories).
+#pragma once
+#include "design_core.cuh"
+#include "kernels.h"
+
+namespace adp {
+
+struct ScoreBatchArgs {
+  ScoreProblemDev sp;
+  const uint8_t* seqs;       // B rows of sp.n bytes
+  int B;
+  double* score;             // [B]
+  double* terms;             // NULL or [B * n_ctx * n_terms]
+  double* gmats;
+  size_t gmat_stride;
+};
+
+struct McArgs {
+  ScoreProblemDev sp;
+  const MoveTableDev* moves;
+  const uint8_t* init_seq;   // sp.n bytes
+  int n_traj;
+  uint64_t seed, traj_id0;
+  int n_steps;
+  int thermo_kind;
+  double thermo_args[3];
+  uint8_t* final_seq;        // each output may be NULL
+  double* final_score;
+  uint8_t* best_seq;
+  double* best_score;
+  int32_t* best_step;
+  uint32_t* outcomes;
+  double* gmats;
+  size_t gmat_stride;
+};
+
+LaunchPlan plan_design(const DeviceInfo&, int n_max, int jobs);
+cudaError_t launch_score(const ScoreBatchArgs&, const LaunchPlan&, cudaStream_t);
+cudaError_t launch_mc(const McArgs&, const LaunchPlan&, cudaStream_t);
+
+}  // namespace adp

@@ -1,0 +1,154 @@
+// One fold job = one construct handled by one CTA: carve the working set out of a raw buffer, stage the
+// context and tables, run the recursions, write the results.  Shared by the CUDA kernels (fold_kernels.cu)
+// and by the single-thread emulation the CPU-only tests use (tests/emu).
+#pragma once
+#include "mfe_core.cuh"
+#include "pf_core.cuh"
+
+namespace adp {
+
+struct Carver {
+  char* p;
+  ADP_HD explicit Carver(void* base) : p((char*)base) {}
+  template <class T>
+  ADP_HD T* take(size_t count) {
+    size_t a = (size_t)p;
+    a = (a + 15) & ~(size_t)15;
+    T* r = (T*)a;
+    p = (char*)a + count * sizeof(T);
+    return r;
+  }
+};
+
+// bytes of the per-construct context arrays
+ADP_HD size_t ctx_bytes(int n) {
+  return 16 * 8 + (size_t)(n + 4) * (1 + 1 + 1) + (size_t)(n + 4) * 2 * 4;
+}
+
+ADP_HD void carve_ctx(Carver& cv, SeqCtx& c, int n) {
+  c.n = n;
+  c.S = cv.take<uint8_t>(n + 4);
+  c.flag = cv.take<uint8_t>(n + 4);
+  c.motif_at = cv.take<uint8_t>(n + 4);
+  c.partner = cv.take<uint16_t>(n + 4);
+  c.enc = cv.take<uint16_t>(n + 4);
+  c.upr = cv.take<uint16_t>(n + 4);
+  c.upl = cv.take<uint16_t>(n + 4);
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct PfJob {
+  const uint8_t* seq;
+  int n;
+  const ConstraintDev* cst;     // NULL = unconstrained
+  const MotifDev* motif;        // NULL = apo
+  const PfTables* T;
+  bool outside;                 // also compute base-pair probabilities
+  double* dG;                   // -> ensemble free energy, kcal/mol
+  double* bppm;                 // NULL or n(n+1)/2 doubles, row-major upper triangle incl. diagonal, 0-based
+  int n_query;                  // pair-probability queries (0-based i,j), answered into qprobs
+  const int32_t* qi;
+  const int32_t* qj;
+  double* qprobs;
+};
+
+ADP_HD size_t pf_small_bytes(int n) { return sizeof(PfSmall) + 16 + ctx_bytes(n) + (size_t)9 * (n + 4) * sizeof(double); }
+ADP_HD size_t pf_matrix_doubles(int n, bool outside) { return (size_t)(outside ? 3 : 2) * ((size_t)n * (n + 1) / 2); }
+
+// `small` : shared memory (pf_small_bytes).  `mats`: shared or global memory (pf_matrix_doubles).
+template <class E>
+ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats) {
+  const int n = job.n;
+  const size_t ntri = (size_t)n * (n + 1) / 2;
+  Carver cv(small);
+  PfSmall* P = cv.take<PfSmall>(1);
+  SeqCtx c;
+  carve_ctx(cv, c, n);
+  PfWork w;
+  w.qm1a = cv.take<double>(n + 4);
+  w.qm1b = cv.take<double>(n + 4);
+  w.q1 = cv.take<double>(n + 4);
+  w.qln = cv.take<double>(n + 4);
+  w.ext = cv.take<double>(n + 4);
+  w.va = cv.take<double>(n + 4);
+  w.vb = cv.take<double>(n + 4);
+  w.vab = cv.take<double>(n + 4);
+  w.qb = mats;
+  w.qm = mats + ntri;
+  w.pr = job.outside ? mats + 2 * ntri : nullptr;
+  w.scale = job.T->scale;
+  w.eMLb = job.T->eMLb;
+  c.has_cst = job.cst != nullptr;
+  c.motif_len = job.motif ? job.motif->len : 0;
+  const double mboltz = job.motif ? job.motif->boltz : 1.;
+  stage_small(ex, P, job.T);
+  load_context(ex, c, job.seq, job.cst, job.motif);   // ends with a barrier
+
+  const double Z = pf_inside(ex, c, *P, job.T, mboltz, w);
+  if (ex.tid() == 0)
+    *job.dG = Z > 0. ? (-log(Z) - n * log(job.T->pf_scale)) * job.T->kT / 1000. : (double)INFINITY;
+  if (!job.outside) return;
+
+  if (Z > 0.) {
+    pf_outside(ex, c, *P, job.T, job.motif, mboltz, w);
+  } else {
+    for (size_t k = ex.tid(); k < ntri; k += ex.nthreads()) w.pr[k] = 0.;
+    ex.sync();
+  }
+  if (job.bppm) {
+    // row-major output: row i0 (0-based) starts at i0*n - i0*(i0-1)/2, entry (i0,j0) at + (j0-i0)
+    for (int i = 1; i <= n; i++) {
+      const size_t row = (size_t)(i - 1) * n - (size_t)(i - 1) * (i - 2) / 2;
+      for (int j = i + ex.tid(); j <= n; j += ex.nthreads()) job.bppm[row + (j - i)] = j > i ? w.pr[tri(i, j)] : 0.;
+    }
+  }
+  for (int q = ex.tid(); q < job.n_query; q += ex.nthreads()) {
+    int a = job.qi[q], b = job.qj[q];
+    if (a > b) { const int t = a; a = b; b = t; }
+    job.qprobs[q] = (a != b && a >= 0 && b < n) ? w.pr[tri(a + 1, b + 1)] : 0.;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct MfeJob {
+  const uint8_t* seq;
+  int n;
+  const ConstraintDev* cst;
+  const MotifDev* motif;
+  const IntTables* T;
+  int32_t* e_dcal;        // -> minimum free energy
+  char* structure;        // NULL or n chars
+};
+
+ADP_HD size_t mfe_small_bytes(int n) { return 16 + ctx_bytes(n) + (size_t)4 * (n + 4) * sizeof(int32_t) + (size_t)(4 * n + 16) * 3 * sizeof(int16_t) + (n + 16); }
+ADP_HD size_t mfe_matrix_ints(int n) { return (size_t)2 * ((size_t)n * (n + 1) / 2); }
+
+template <class E>
+ADP_HD void run_mfe_job(const E& ex, const MfeJob& job, void* small, int32_t* mats) {
+  const int n = job.n;
+  const size_t ntri = (size_t)n * (n + 1) / 2;
+  Carver cv(small);
+  SeqCtx c;
+  carve_ctx(cv, c, n);
+  MfeWork w;
+  w.fm1a = cv.take<int32_t>(n + 4);
+  w.fm1b = cv.take<int32_t>(n + 4);
+  w.f5 = cv.take<int32_t>(n + 4);
+  w.ext = cv.take<int32_t>(n + 4);
+  w.stack = cv.take<int16_t>((size_t)(4 * n + 16) * 3);
+  w.out = cv.take<char>(n + 16);
+  w.C = mats;
+  w.F = mats + ntri;
+  c.has_cst = job.cst != nullptr;
+  c.motif_len = job.motif ? job.motif->len : 0;
+  const int mdcal = job.motif ? job.motif->contrib_dcal : 0;
+  load_context(ex, c, job.seq, job.cst, job.motif);
+  const int e = mfe_fill(ex, c, *job.T, mdcal, w);
+  if (ex.tid() == 0) *job.e_dcal = e;
+  if (!job.structure) return;
+  if (ex.warp() == 0) mfe_traceback(ex, c, *job.T, job.motif, mdcal, w);
+  ex.sync();
+  for (int p = ex.tid(); p < n; p += ex.nthreads()) job.structure[p] = w.out[p];
+}
+
+}  // namespace adp

@@ -1,0 +1,173 @@
+// sm_100a kernels for batched folds: one construct per CTA, persistent CTAs striding over the job list.
+// The recursions live in pf_core.cuh / mfe_core.cuh; this file binds them to a CTA, shared memory and the
+// batch layout.  No tensor cores (the recursions are not dense contractions), no library calls.
+#include "fold_jobs.cuh"
+#include "kernels.h"
+
+namespace adp {
+
+extern __shared__ __align__(16) unsigned char adp_smem[];
+
+template <int G, bool kSmemMats>
+__global__ void __launch_bounds__(512) pf_batch_kernel(const PfBatchArgs a) {
+  CtaExec<G> ex;
+  const int n = a.n;
+  const size_t ntri = (size_t)n * (n + 1) / 2;
+  const int jobs = a.B * a.V;
+  void* small = adp_smem;
+  double* mats;
+  if (kSmemMats) {
+    size_t off = (pf_small_bytes(n) + 15) & ~(size_t)15;
+    mats = reinterpret_cast<double*>(adp_smem + off);
+  } else {
+    mats = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
+  }
+  for (int jid = blockIdx.x; jid < jobs; jid += gridDim.x) {
+    const int b = jid / a.V, v = jid - b * a.V;
+    const VariantDev var = a.variants[v];
+    PfJob job;
+    job.seq = a.seqs + (size_t)b * n;
+    job.n = n;
+    job.cst = var.cst_id >= 0 ? a.csts + var.cst_id : nullptr;
+    job.motif = var.use_motif ? a.motif : nullptr;
+    job.T = a.T;
+    job.outside = var.outside != 0;
+    job.dG = a.dG + jid;
+    job.bppm = (a.bppm && job.outside) ? a.bppm + (size_t)jid * ntri : nullptr;
+    job.n_query = job.outside ? a.n_query : 0;
+    job.qi = a.qi;
+    job.qj = a.qj;
+    job.qprobs = a.qprobs ? a.qprobs + (size_t)jid * a.n_query : nullptr;
+    run_pf_job(ex, job, small, mats);
+    __syncthreads();   // the next job reuses the working set
+  }
+}
+
+template <int G, bool kSmemMats>
+__global__ void __launch_bounds__(512) mfe_batch_kernel(const MfeBatchArgs a) {
+  CtaExec<G> ex;
+  const int n = a.n;
+  void* small = adp_smem;
+  int32_t* mats;
+  if (kSmemMats) {
+    size_t off = (mfe_small_bytes(n) + 15) & ~(size_t)15;
+    mats = reinterpret_cast<int32_t*>(adp_smem + off);
+  } else {
+    mats = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
+  }
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    MfeJob job;
+    job.seq = a.seqs + (size_t)b * n;
+    job.n = n;
+    job.cst = a.cst;
+    job.motif = a.motif;
+    job.T = a.T;
+    job.e_dcal = a.e_dcal + b;
+    job.structure = a.structs ? a.structs + (size_t)b * n : nullptr;
+    run_mfe_job(ex, job, small, mats);
+    __syncthreads();
+  }
+}
+
+// Register-resident FP64 FMA loop: the measured denominator of the SM-issue roofline.
+__global__ void dfma_probe_kernel(double* out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;
+  double a4 = a0 + 4e-9, a5 = a0 + 5e-9, a6 = a0 + 6e-9, a7 = a0 + 7e-9;
+  const double m = 0.999999999, c = 1e-12;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// ---------------------------------------------------------------------------------------------------
+static void pick_shape(int n, int* threads, int* group) {
+  // lanes per cell x cell slots: keep one pass per column where the thread budget allows it
+  if (n <= 68) { *threads = 256; *group = 4; }
+  else if (n <= 132) { *threads = 256; *group = 2; }
+  else if (n <= 260) { *threads = 512; *group = 2; }
+  else { *threads = 512; *group = 1; }
+}
+
+static LaunchPlan plan_common(const DeviceInfo& d, int n, int jobs, size_t small, size_t mats_bytes) {
+  LaunchPlan p{};
+  pick_shape(n, &p.threads, &p.group);
+  const size_t small_al = (small + 15) & ~(size_t)15;
+  const size_t both = small_al + mats_bytes;
+  p.mats_in_smem = both <= d.smem_optin;
+  p.smem_bytes = p.mats_in_smem ? both : small_al;
+  size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);   // 1 KB reserved per resident CTA
+  size_t by_threads = 2048 / p.threads;
+  size_t occ = per_sm < by_threads ? per_sm : by_threads;
+  if (occ < 1) occ = 1;
+  long grid = (long)d.sm_count * (long)occ;
+  if (grid > jobs) grid = jobs;
+  if (grid < 1) grid = 1;
+  p.grid = (int)grid;
+  return p;
+}
+
+LaunchPlan plan_pf(const DeviceInfo& d, int n, int jobs, bool any_outside) {
+  const size_t nd = pf_matrix_doubles(n, any_outside);
+  LaunchPlan p = plan_common(d, n, jobs, pf_small_bytes(n), nd * sizeof(double));
+  p.gmat_stride = p.mats_in_smem ? 0 : nd;
+  return p;
+}
+
+LaunchPlan plan_mfe(const DeviceInfo& d, int n, int jobs) {
+  const size_t ni = mfe_matrix_ints(n);
+  LaunchPlan p = plan_common(d, n, jobs, mfe_small_bytes(n), ni * sizeof(int32_t));
+  p.gmat_stride = p.mats_in_smem ? 0 : ni;
+  return p;
+}
+
+template <class K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+#define ADP_LAUNCH(KERNEL, ARGS)                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = set_smem(KERNEL, p.smem_bytes);                                    \
+    if (e_ != cudaSuccess) return e_;                                                   \
+    KERNEL<<<p.grid, p.threads, p.smem_bytes, stream>>>(ARGS);                          \
+    return cudaGetLastError();                                                          \
+  } while (0)
+
+cudaError_t launch_pf(const PfBatchArgs& a, const LaunchPlan& p, cudaStream_t stream) {
+  if (p.mats_in_smem) {
+    switch (p.group) {
+      case 4: ADP_LAUNCH((pf_batch_kernel<4, true>), a);
+      case 2: ADP_LAUNCH((pf_batch_kernel<2, true>), a);
+      default: ADP_LAUNCH((pf_batch_kernel<1, true>), a);
+    }
+  }
+  switch (p.group) {
+    case 4: ADP_LAUNCH((pf_batch_kernel<4, false>), a);
+    case 2: ADP_LAUNCH((pf_batch_kernel<2, false>), a);
+    default: ADP_LAUNCH((pf_batch_kernel<1, false>), a);
+  }
+}
+
+cudaError_t launch_mfe(const MfeBatchArgs& a, const LaunchPlan& p, cudaStream_t stream) {
+  if (p.mats_in_smem) {
+    switch (p.group) {
+      case 4: ADP_LAUNCH((mfe_batch_kernel<4, true>), a);
+      case 2: ADP_LAUNCH((mfe_batch_kernel<2, true>), a);
+      default: ADP_LAUNCH((mfe_batch_kernel<1, true>), a);
+    }
+  }
+  switch (p.group) {
+    case 4: ADP_LAUNCH((mfe_batch_kernel<4, false>), a);
+    case 2: ADP_LAUNCH((mfe_batch_kernel<2, false>), a);
+    default: ADP_LAUNCH((mfe_batch_kernel<1, false>), a);
+  }
+}
+
+cudaError_t launch_dfma_probe(double* out, int iters, int grid, int threads, cudaStream_t stream) {
+  dfma_probe_kernel<<<grid, threads, 0, stream>>>(out, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace adp

@@ -1,0 +1,137 @@
+// Host-side compilation of a design problem (adp_problem of include/addapt_b200.h) into the flat records
+// the design kernels read: contexts and their padded constraints, the list of distinct ensemble fills
+// ("variants") the score terms need, and the mutation closures.
+//   contexts / macrostate padding   ≙ Device::context, Device::macrostate      (reference src/model.cc:43-51)
+//   term -> (condition, macrostate) ≙ MacrostateProbTerm                        (reference src/scoring.cc:204-259)
+//   free positions                  ≙ can_be_mutated / can_be_freely_mutated    (reference src/sampling.cc:170-193)
+//   closures                        ≙ mutate_recursively                        (reference src/sampling.cc:205-282)
+#pragma once
+#include <cctype>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/addapt_b200.h"
+#include "constraints.h"
+#include "design_core.cuh"
+
+namespace adp {
+
+struct CompiledProblem {
+  ScoreProblemDev sp;                    // sp.csts / sp.motif / sp.T are filled in by the caller
+  std::vector<ConstraintDev> csts;       // [n_ctx][n_macro]
+  bool has_motif = false;
+};
+
+// Throws std::string on malformed input.
+inline void compile_problem(const adp_problem& pr, double kT_kcal, CompiledProblem* out) {
+  ScoreProblemDev& sp = out->sp;
+  std::memset(&sp, 0, sizeof sp);
+  if (pr.n < 1 || pr.n > ADP_MAX_LEN) throw std::string("device length out of range");
+  if (pr.n_macro < 0 || pr.n_macro > kMaxMacro) throw std::string("too many macrostates (max 8)");
+  if (pr.n_terms < 0 || pr.n_terms > kMaxTerms) throw std::string("too many score terms (max 16)");
+  if (pr.n_ctx < 0 || pr.n_ctx > kMaxCtx) throw std::string("too many contexts (max 8)");
+  sp.n = pr.n;
+  sp.n_ctx = pr.n_ctx > 0 ? pr.n_ctx : 1;
+  sp.n_macro = pr.n_macro;
+  sp.n_terms = pr.n_terms;
+  sp.float_dg = pr.float_dg;
+  sp.kT = kT_kcal;
+  out->has_motif = pr.motif.seq != nullptr;
+  sp.n_max = 0;
+  for (int x = 0; x < sp.n_ctx; x++) {
+    std::string bef = pr.n_ctx > 0 && pr.ctx_before && pr.ctx_before[x] ? pr.ctx_before[x] : "";
+    std::string aft = pr.n_ctx > 0 && pr.ctx_after && pr.ctx_after[x] ? pr.ctx_after[x] : "";
+    if (bef.size() > (size_t)kMaxFlank || aft.size() > (size_t)kMaxFlank) throw std::string("context flank longer than 64 nt");
+    sp.nb[x] = (int)bef.size();
+    sp.na[x] = (int)aft.size();
+    for (size_t k = 0; k < bef.size(); k++) sp.before[x][k] = (uint8_t)bef[k];
+    for (size_t k = 0; k < aft.size(); k++) sp.after[x][k] = (uint8_t)aft[k];
+    const int nx = sp.nb[x] + sp.n + sp.na[x];
+    if (nx > ADP_MAX_LEN) throw std::string("device + context longer than the engine's maximum length");
+    if (nx > sp.n_max) sp.n_max = nx;
+  }
+  out->csts.resize((size_t)sp.n_ctx * (sp.n_macro > 0 ? sp.n_macro : 1));
+  for (int x = 0; x < sp.n_ctx; x++)
+    for (int m = 0; m < sp.n_macro; m++) {
+      if (!pr.macro_cst || !pr.macro_cst[m]) throw std::string("missing macrostate constraint");
+      std::string c(pr.macro_cst[m]);
+      if ((int)c.size() != pr.n) throw std::string("macrostate constraint length differs from the device length");
+      std::string padded = std::string(sp.nb[x], '.') + c + std::string(sp.na[x], '.');     // model.cc:43-51
+      build_constraint(padded, (int)padded.size(), &out->csts[(size_t)x * sp.n_macro + m]);
+    }
+  // distinct fills: (condition, none) and (condition, macrostate)
+  auto find_or_add = [&](int cond, int macro) {
+    const int use_motif = (cond == 1 && out->has_motif) ? 1 : 0;
+    for (int v = 0; v < sp.V; v++)
+      if (sp.variants[v].cst_id == macro && sp.variants[v].use_motif == use_motif) return v;
+    if (sp.V >= kMaxVariants) throw std::string("score function needs more than 8 distinct ensemble fills");
+    sp.variants[sp.V] = VariantDev{macro, use_motif, 0, 0};
+    return sp.V++;
+  };
+  for (int t = 0; t < sp.n_terms; t++) {
+    const int macro = pr.term_macro[t], cond = pr.term_cond[t];
+    if (macro < 0 || macro >= sp.n_macro) throw std::string("score term refers to an unknown macrostate");
+    if (cond != 0 && cond != 1) throw std::string("score term condition must be 0 (apo) or 1 (holo)");
+    sp.term_fav[t] = pr.term_favorable[t] ? 1 : 0;
+    sp.term_w[t] = pr.term_weight[t];
+    sp.term_v0[t] = find_or_add(cond, -1);
+    sp.term_v1[t] = find_or_add(cond, macro);
+  }
+}
+
+// Throws std::string when a drawn mutation could not be applied (the reference would throw at that step).
+inline void compile_moves(const adp_problem& pr, MoveTableDev* mv) {
+  std::memset(mv, 0, sizeof *mv);
+  const int n = pr.n;
+  const std::string seq(pr.init_seq, pr.init_seq + n);
+  std::vector<std::string> macros;
+  for (int m = 0; m < pr.n_macro; m++) macros.emplace_back(pr.macro_cst[m]);
+  auto mutable_at = [&](int p) { return std::isupper((unsigned char)seq[p]) != 0; };
+  for (int i = 0; i < n; i++) {
+    if (!mutable_at(i)) continue;
+    bool free_pos = true;
+    for (auto& ms : macros) if (ms[i] == ')') free_pos = false;
+    if (!free_pos) continue;
+    // closure of i: alternate nucleotide / complement along every bracket partner, in every macrostate
+    std::vector<int> parity(n, -1), order;
+    std::vector<std::pair<int, int>> todo{{i, 0}};
+    parity[i] = 0;
+    order.push_back(i);
+    for (size_t head = 0; head < todo.size(); head++) {
+      const int p = todo[head].first, par = todo[head].second;
+      for (auto& ms : macros) {
+        char open, close;
+        int dir;
+        if (ms[p] == '(') { open = '('; close = ')'; dir = 1; }
+        else if (ms[p] == ')') { open = ')'; close = '('; dir = -1; }
+        else continue;
+        int level = 1, q = p;
+        while (level) {
+          q += dir;
+          if (q < 0 || q >= n) throw std::string("mismatched base-pair in a macrostate");
+          if (ms[q] == open) level++;
+          else if (ms[q] == close) level--;
+        }
+        if (!mutable_at(q)) throw std::string("position ") + std::to_string(i) + " cannot be mutated: its partner " + std::to_string(q) + " is not mutable";
+        if (parity[q] < 0) {
+          parity[q] = par ^ 1;
+          order.push_back(q);
+          todo.emplace_back(q, par ^ 1);
+        } else if (parity[q] != (par ^ 1)) {
+          throw std::string("macrostates impose unsatisfiable base-pairing on position ") + std::to_string(i);
+        }
+      }
+    }
+    if ((int)order.size() > kMaxClosure) throw std::string("a mutation would change more than 16 positions");
+    const int slot = mv->n_free++;
+    mv->free_pos[slot] = (int16_t)i;
+    mv->closure_len[slot] = (int8_t)order.size();
+    for (size_t k = 0; k < order.size(); k++) {
+      mv->closure_pos[slot][k] = (int16_t)order[k];
+      mv->closure_comp[slot][k] = (int8_t)parity[order[k]];
+    }
+  }
+}
+
+}  // namespace adp

@@ -1,0 +1,142 @@
+// tests/emu/emu.cc -- TEST INFRASTRUCTURE ONLY; never part of libaddapt_b200.so.
+//
+// Compiles the engine's kernel bodies (addapt_b200/csrc/*_core.cuh, fold_jobs.cuh) for the host with the
+// single-thread SerialExec policy, so the recursions, constraint handling and traceback can be checked
+// against the oracle on a machine without a GPU (pytest -m "not gpu").  It exercises the same source the
+// sm_100a kernels are built from, but not their parallel decomposition -- that is what the -m gpu tests do.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../addapt_b200/csrc/constraints.h"
+#include "../../addapt_b200/csrc/design_core.cuh"
+#include "../../addapt_b200/csrc/energy_model.h"
+#include "../../addapt_b200/csrc/fold_jobs.cuh"
+#include "../../addapt_b200/csrc/problem_host.h"
+
+using namespace adp;
+
+static std::string g_err;
+
+extern "C" {
+
+const char* emu_error() { return g_err.c_str(); }
+
+void* emu_model_load(const char* par) {
+  try {
+    auto* m = new EnergyModel();
+    m->load(par);
+    return m;
+  } catch (std::string& e) { g_err = e; return nullptr; }
+}
+
+double emu_kT(void* model) { return ((EnergyModel*)model)->kT_kcal(); }
+
+int emu_eval(void* model, const char* seq, const char* db, int* e) {
+  try { *e = ((EnergyModel*)model)->eval_structure(seq, db); return 0; } catch (std::string& er) { g_err = er; return -1; }
+}
+
+int emu_motif_contrib(void* model, const char* mseq, const char* mfold, double kd_uM, int* c) {
+  auto* M = (EnergyModel*)model;
+  try { *c = M->make_motif(mseq, mfold, M->kT_kcal() * std::log(kd_uM / 1e6)).contrib_dcal; return 0; } catch (std::string& er) { g_err = er; return -1; }
+}
+
+int emu_pf(void* model, int n, const char* seq, const char* cst, const char* mseq, const char* mfold, double kd_uM,
+           int outside, double* dG, double* bppm) {
+  auto* M = (EnergyModel*)model;
+  try {
+    ConstraintDev cd;
+    MotifDev md;
+    if (cst) build_constraint(cst, n, &cd);
+    if (mseq) md = M->make_motif(mseq, mfold, M->kT_kcal() * std::log(kd_uM / 1e6));
+    PfJob job{};
+    job.seq = (const uint8_t*)seq; job.n = n; job.cst = cst ? &cd : nullptr; job.motif = mseq ? &md : nullptr;
+    job.T = &M->pf(); job.outside = outside != 0; job.dG = dG; job.bppm = bppm;
+    std::vector<char> small(pf_small_bytes(n) + 64);
+    std::vector<double> mats(pf_matrix_doubles(n, job.outside) + 2);
+    SerialExec ex;
+    run_pf_job(ex, job, small.data(), mats.data());
+    return 0;
+  } catch (std::string& er) { g_err = er; return -1; }
+}
+
+int emu_mfe(void* model, int n, const char* seq, const char* cst, const char* mseq, const char* mfold, double kd_uM,
+            int32_t* e, char* structure) {
+  auto* M = (EnergyModel*)model;
+  try {
+    ConstraintDev cd;
+    MotifDev md;
+    if (cst) build_constraint(cst, n, &cd);
+    if (mseq) md = M->make_motif(mseq, mfold, M->kT_kcal() * std::log(kd_uM / 1e6));
+    MfeJob job{};
+    job.seq = (const uint8_t*)seq; job.n = n; job.cst = cst ? &cd : nullptr; job.motif = mseq ? &md : nullptr;
+    job.T = &M->mfe(); job.e_dcal = e; job.structure = structure;
+    std::vector<char> small(mfe_small_bytes(n) + 64);
+    std::vector<int32_t> mats(mfe_matrix_ints(n) + 2);
+    SerialExec ex;
+    run_mfe_job(ex, job, small.data(), mats.data());
+    return 0;
+  } catch (std::string& er) { g_err = er; return -1; }
+}
+
+// score of B sequences of one design problem (adp_problem layout of include/addapt_b200.h)
+int emu_score(void* model, const adp_problem* pr, int B, const char* seqs, double* score, double* terms) {
+  auto* M = (EnergyModel*)model;
+  try {
+    CompiledProblem cp;
+    compile_problem(*pr, M->kT_kcal(), &cp);
+    MotifDev md;
+    if (pr->motif.seq) { md = M->make_motif(pr->motif.seq, pr->motif.fold, M->kT_kcal() * std::log(pr->motif.kd_uM / 1e6)); cp.sp.motif = &md; }
+    cp.sp.csts = cp.csts.data();
+    cp.sp.T = &M->pf();
+    const int nm = cp.sp.n_max;
+    std::vector<char> small(pf_small_bytes(nm) + 64), extra(design_extra_bytes(nm) + 256);
+    std::vector<double> mats(pf_matrix_doubles(nm, false) + 2);
+    Carver cv(extra.data());
+    DesignScratch d;
+    carve_design(cv, d, nm);
+    SerialExec ex;
+    const int nt = cp.sp.n_ctx * cp.sp.n_terms;
+    for (int b = 0; b < B; b++) {
+      std::memcpy(d.cur, seqs + (size_t)b * pr->n, pr->n);
+      score[b] = score_construct(ex, cp.sp, d.cur, d, small.data(), mats.data());
+      if (terms) for (int t = 0; t < nt; t++) terms[(size_t)b * nt + t] = d.terms[t];
+    }
+    return 0;
+  } catch (std::string& er) { g_err = er; return -1; }
+}
+
+int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, int n_steps, int kind, const double* targs,
+           char* final_seq, double* final_score, char* best_seq, double* best_score, int32_t* best_step, uint32_t* outcomes) {
+  auto* M = (EnergyModel*)model;
+  try {
+    CompiledProblem cp;
+    compile_problem(*pr, M->kT_kcal(), &cp);
+    MotifDev md;
+    if (pr->motif.seq) { md = M->make_motif(pr->motif.seq, pr->motif.fold, M->kT_kcal() * std::log(pr->motif.kd_uM / 1e6)); cp.sp.motif = &md; }
+    cp.sp.csts = cp.csts.data();
+    cp.sp.T = &M->pf();
+    std::vector<MoveTableDev> mv(1);
+    compile_moves(*pr, &mv[0]);
+    const int nm = cp.sp.n_max;
+    std::vector<char> small(pf_small_bytes(nm) + 64), extra(design_extra_bytes(nm) + 256);
+    std::vector<double> mats(pf_matrix_doubles(nm, false) + 2);
+    Carver cv(extra.data());
+    DesignScratch d;
+    carve_design(cv, d, nm);
+    SerialExec ex;
+    std::memcpy(d.cur, pr->init_seq, pr->n);
+    McResult res;
+    double ta[3] = {targs[0], kind == 1 ? targs[1] : 0., kind == 1 ? targs[2] : 1.};
+    mc_trajectory(ex, cp.sp, mv[0], seed, traj_id, n_steps, kind, ta, d, small.data(), mats.data(), &res);
+    std::memcpy(final_seq, d.cur, pr->n);
+    std::memcpy(best_seq, d.best, pr->n);
+    *final_score = res.final_score; *best_score = res.best_score; *best_step = res.best_step;
+    for (int k = 0; k < 4; k++) outcomes[k] = res.outcomes[k];
+    return 0;
+  } catch (std::string& er) { g_err = er; return -1; }
+}
+
+}  // extern "C"

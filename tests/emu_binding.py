@@ -1,0 +1,93 @@
+"""ctypes binding of tests/emu/libadp_emu.so -- TEST INFRASTRUCTURE (see tests/emu/emu.cc)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from addapt_b200.capi import DEFAULT_PAR, Problem, _Problem, _b
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Emu:
+    def __init__(self, par=None):
+        L = self.lib = C.CDLL(os.path.join(HERE, "emu", "libadp_emu.so"))
+        L.emu_model_load.restype = C.c_void_p
+        L.emu_model_load.argtypes = [C.c_char_p]
+        L.emu_error.restype = C.c_char_p
+        L.emu_kT.restype = C.c_double
+        L.emu_kT.argtypes = [C.c_void_p]
+        L.emu_eval.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.emu_motif_contrib.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_int)]
+        L.emu_pf.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_int,
+                             C.POINTER(C.c_double), C.c_void_p]
+        L.emu_mfe.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double,
+                              C.POINTER(C.c_int32), C.c_char_p]
+        L.emu_score.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_int, C.c_char_p, C.c_void_p, C.c_void_p]
+        L.emu_mc.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double),
+                             C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                             C.POINTER(C.c_uint32)]
+        self.model = L.emu_model_load(_b(par or DEFAULT_PAR))
+        if not self.model:
+            raise RuntimeError(L.emu_error().decode())
+        self.kT = L.emu_kT(self.model)
+
+    def _err(self):
+        return ValueError(self.lib.emu_error().decode())
+
+    def eval_structure(self, seq, db):
+        e = C.c_int()
+        if self.lib.emu_eval(self.model, _b(seq), _b(db), C.byref(e)):
+            raise self._err()
+        return e.value
+
+    def motif_contribution(self, motif):
+        c = C.c_int()
+        if self.lib.emu_motif_contrib(self.model, _b(motif[0]), _b(motif[1]), motif[2], C.byref(c)):
+            raise self._err()
+        return c.value
+
+    def pf(self, seq, cst=None, motif=None, bppm=False):
+        n = len(seq)
+        dg = C.c_double()
+        bp = np.zeros(n * (n + 1) // 2)
+        rc = self.lib.emu_pf(self.model, n, _b(seq), _b(cst) if cst else None, _b(motif[0]) if motif else None,
+                             _b(motif[1]) if motif else None, motif[2] if motif else 0.0, 1 if bppm else 0, C.byref(dg),
+                             bp.ctypes.data)
+        if rc:
+            raise self._err()
+        return (dg.value, bp) if bppm else dg.value
+
+    def mfe(self, seq, cst=None, motif=None):
+        n = len(seq)
+        e = C.c_int32()
+        st = C.create_string_buffer(n + 1)
+        rc = self.lib.emu_mfe(self.model, n, _b(seq), _b(cst) if cst else None, _b(motif[0]) if motif else None,
+                              _b(motif[1]) if motif else None, motif[2] if motif else 0.0, C.byref(e), st)
+        if rc:
+            raise self._err()
+        return e.value, st.raw[:n].decode()
+
+    def score(self, problem: Problem, seqs, want_terms=False):
+        B = len(seqs)
+        flat = b"".join(_b(s) for s in seqs)
+        out = np.zeros(B)
+        terms = np.zeros((B, problem.n_term_values))
+        if self.lib.emu_score(self.model, C.byref(problem.c), B, flat, out.ctypes.data, terms.ctypes.data):
+            raise self._err()
+        return (out, terms) if want_terms else out
+
+    def mc_run(self, problem: Problem, seed, traj_id, n_steps, thermostat=("annealing", 5.0, 0.0, 300)):
+        n = problem.n
+        if thermostat[0] == "fixed":
+            kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
+        else:
+            kind, ta = 1, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
+        fs, bs = C.create_string_buffer(n + 1), C.create_string_buffer(n + 1)
+        fsc, bsc, bst = C.c_double(), C.c_double(), C.c_int32()
+        oc = (C.c_uint32 * 4)()
+        if self.lib.emu_mc(self.model, C.byref(problem.c), seed, traj_id, n_steps, kind, ta, fs, C.byref(fsc), bs, C.byref(bsc),
+                           C.byref(bst), oc):
+            raise self._err()
+        return dict(final_seq=fs.raw[:n].decode(), final_score=fsc.value, best_seq=bs.raw[:n].decode(), best_score=bsc.value,
+                    best_step=bst.value, outcomes=list(oc))
