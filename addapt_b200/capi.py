@@ -93,6 +93,7 @@ def load_library():
     L.adp_engine_set_stream.argtypes = [vp, vp]
     L.adp_engine_set_async.argtypes = [vp, ci]
     L.adp_engine_sync.argtypes = [vp]
+    L.adp_engine_set_general_only.argtypes = [vp, ci]
     L.adp_kT_kcal.argtypes = [vp]
     L.adp_kT_kcal.restype = cd
     L.adp_device_count.restype = ci
@@ -177,6 +178,10 @@ class Engine:
 
     def set_async(self, flag):
         self._check(self.lib.adp_engine_set_async(self.h, int(flag)))
+
+    def set_general_only(self, flag):
+        """route folds through the general kernels instead of the fast ACGU-only ones (parity tests)"""
+        self._check(self.lib.adp_engine_set_general_only(self.h, int(flag)))
 
     def sync(self):
         self._check(self.lib.adp_engine_sync(self.h))

@@ -110,8 +110,11 @@ ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
 
 // Score of the raw sequence `raw` (n ASCII bytes, readable by every thread).  Collective; every thread gets
 // the score.  Unweighted term values are left in d.terms[ctx*n_terms + t].
-template <class E>
-ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint8_t* raw, DesignScratch& d, void* fold_small, double* mats) {
+// kFast: fold with pf_fast.cuh (fold_small / mats sized by fast_small_bytes / fast_matrix_doubles); *declined is
+// set (and the score is meaningless) when a sequence holds letters outside ACGU/T.
+template <bool kFast, class E>
+ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint8_t* raw, DesignScratch& d, void* fold_small, double* mats,
+                              bool* declined = nullptr, double* dstate = nullptr) {
   double score = 0.;
   for (int x = 0; x < sp.n_ctx; x++) {
     const int nb = sp.nb[x], na = sp.na[x], nx = nb + sp.n + na;
@@ -131,7 +134,14 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
       job.bppm = nullptr;
       job.n_query = 0;
       job.qi = nullptr; job.qj = nullptr; job.qprobs = nullptr;
-      run_pf_job(ex, job, fold_small, mats);
+      if constexpr (kFast) {
+        if (!run_pf_job_fast(ex, job, fold_small, mats, dstate)) {
+          if (declined) *declined = true;
+          return 0.;
+        }
+      } else {
+        run_pf_job(ex, job, fold_small, mats);
+      }
       ex.sync();
     }
     if (ex.tid() == 0) {
@@ -155,12 +165,14 @@ struct McResult {
   uint32_t outcomes[4];      // REJECT, ACCEPT_WORSENED, ACCEPT_UNCHANGED, ACCEPT_IMPROVED
 };
 
-// One trajectory.  d.cur must hold the start sequence (upper case).  Collective.
-template <class E>
+// One trajectory.  d.cur must hold the start sequence (upper case).  Collective.  kFast requires ACGU/T-only
+// start sequence and contexts (checked on the host).
+template <bool kFast, class E>
 ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTableDev& mv, uint64_t seed, uint64_t traj_id, int n_steps,
-                          int thermo_kind, const double* thermo_args, DesignScratch& d, void* fold_small, double* mats, McResult* res) {
+                          int thermo_kind, const double* thermo_args, DesignScratch& d, void* fold_small, double* mats, McResult* res,
+                          double* dstate = nullptr) {
   const int n = sp.n;
-  double cur_s = score_construct(ex, sp, d.cur, d, fold_small, mats);
+  double cur_s = score_construct<kFast>(ex, sp, d.cur, d, fold_small, mats, nullptr, dstate);
   double best_s = cur_s;
   int best_step = -1;
   uint32_t oc0 = 0, oc1 = 0, oc2 = 0, oc3 = 0;
@@ -188,7 +200,7 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
       for (int q = 0; q < clen; q++) d.prop[mv.closure_pos[slot][q]] = mv.closure_comp[slot][q] ? ntc : nt;
     ex.sync();
     if (!changed) { oc2++; continue; }                                         // ACCEPT_UNCHANGED: not scored
-    const double prop_s = score_construct(ex, sp, d.prop, d, fold_small, mats);
+    const double prop_s = score_construct<kFast>(ex, sp, d.prop, d, fold_small, mats, nullptr, dstate);
     const double diff = prop_s - cur_s;
     const double crit = exp(diff / T);
     if (crit < u) { oc0++; continue; }                                         // REJECT (NaN compares false: accept)

@@ -12,11 +12,11 @@ struct DesignSmem {
   DesignScratch d;
 };
 
-template <bool kSmemMats>
+template <bool kFast, bool kSmemMats>
 __device__ __forceinline__ DesignSmem carve_design_smem(int n_max, double* gmats, size_t gmat_stride) {
   DesignSmem s;
   s.fold_small = adp_dsmem;
-  size_t off = (pf_small_bytes(n_max) + 15) & ~(size_t)15;
+  size_t off = ((kFast ? fast_small_bytes(n_max) : pf_small_bytes(n_max)) + 15) & ~(size_t)15;
   Carver cv(adp_dsmem + off);
   carve_design(cv, s.d, n_max);
   if (kSmemMats) {
@@ -27,32 +27,40 @@ __device__ __forceinline__ DesignSmem carve_design_smem(int n_max, double* gmats
   return s;
 }
 
-template <int G, bool kSmemMats>
+// kFast: folds with pf_fast.cuh (G must be 1); designs it declines are flagged in a.redo for the general variant.
+template <bool kFast, int G, bool kSmemMats>
 __global__ void __launch_bounds__(512) score_batch_kernel(const ScoreBatchArgs a) {
   CtaExec<G> ex;
-  DesignSmem s = carve_design_smem<kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
+  DesignSmem s = carve_design_smem<kFast, kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
   const int n = a.sp.n, nt_terms = a.sp.n_ctx * a.sp.n_terms;
+  if (!kFast && a.only_redo && a.redo[a.B] == 0) return;
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    if (!kFast && a.only_redo && !a.redo[b]) continue;
     for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.seqs[(size_t)b * n + p];
     __syncthreads();
-    const double sc = score_construct(ex, a.sp, s.d.cur, s.d, s.fold_small, s.mats);
-    if (threadIdx.x == 0) a.score[b] = sc;
-    if (a.terms)
-      for (int t = threadIdx.x; t < nt_terms; t += blockDim.x) a.terms[(size_t)b * nt_terms + t] = s.d.terms[t];
+    bool declined = false;
+    const double sc = score_construct<kFast>(ex, a.sp, s.d.cur, s.d, s.fold_small, s.mats, &declined);
+    if (declined) {
+      if (threadIdx.x == 0) { a.redo[b] = 1; atomicAdd(a.redo + a.B, 1); }
+    } else {
+      if (threadIdx.x == 0) a.score[b] = sc;
+      if (a.terms)
+        for (int t = threadIdx.x; t < nt_terms; t += blockDim.x) a.terms[(size_t)b * nt_terms + t] = s.d.terms[t];
+    }
     __syncthreads();
   }
 }
 
-template <int G, bool kSmemMats>
+template <bool kFast, int G, bool kSmemMats>
 __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
   CtaExec<G> ex;
-  DesignSmem s = carve_design_smem<kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
+  DesignSmem s = carve_design_smem<kFast, kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
   __shared__ McResult res;
   const int n = a.sp.n;
   for (int t = blockIdx.x; t < a.n_traj; t += gridDim.x) {
     for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.init_seq[p];
     __syncthreads();
-    mc_trajectory(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.n_steps, a.thermo_kind, a.thermo_args, s.d, s.fold_small, s.mats, &res);
+    mc_trajectory<kFast>(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.n_steps, a.thermo_kind, a.thermo_args, s.d, s.fold_small, s.mats, &res);
     __syncthreads();
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
       if (a.final_seq) a.final_seq[(size_t)t * n + p] = s.d.cur[p];
@@ -69,16 +77,20 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
   }
 }
 
-LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs) {
-  LaunchPlan p = plan_pf(d, n_max, jobs, false);
+LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs, bool fast) {
+  LaunchPlan p = fast ? plan_pf_fast(d, n_max, jobs) : plan_pf(d, n_max, jobs, false);
+  if (fast && !p.threads) return p;
   // same shape as an inside-only fold, plus the design scratch
-  const size_t small = ((pf_small_bytes(n_max) + 15) & ~(size_t)15) + design_extra_bytes(n_max) + 64;
-  const size_t mats = pf_matrix_doubles(n_max, false) * sizeof(double);
+  const size_t fold_small = fast ? fast_small_bytes(n_max) : pf_small_bytes(n_max);
+  const size_t nmat = fast ? fast_matrix_doubles(n_max) : pf_matrix_doubles(n_max, false);
+  const size_t small = ((fold_small + 15) & ~(size_t)15) + design_extra_bytes(n_max) + 64;
+  const size_t mats = nmat * sizeof(double);
   p.mats_in_smem = small + mats <= d.smem_optin;
   p.smem_bytes = p.mats_in_smem ? small + mats : small;
-  p.gmat_stride = p.mats_in_smem ? 0 : pf_matrix_doubles(n_max, false);
+  p.gmat_stride = p.mats_in_smem ? 0 : nmat;
   size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);
   size_t by_threads = 2048 / p.threads;
+  if (fast && by_threads > 2) by_threads = 2;               // 128 registers per thread
   size_t occ = per_sm < by_threads ? per_sm : by_threads;
   if (occ < 1) occ = 1;
   long grid = (long)d.sm_count * (long)occ;
@@ -96,33 +108,41 @@ LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs) {
     return cudaGetLastError();                                                                            \
   } while (0)
 
-cudaError_t launch_score(const ScoreBatchArgs& a, const LaunchPlan& p, cudaStream_t stream) {
+cudaError_t launch_score(const ScoreBatchArgs& a, const LaunchPlan& p, bool fast, cudaStream_t stream) {
+  if (fast) {
+    if (p.mats_in_smem) ADP_DLAUNCH((score_batch_kernel<true, 1, true>), a);
+    ADP_DLAUNCH((score_batch_kernel<true, 1, false>), a);
+  }
   if (p.mats_in_smem) {
     switch (p.group) {
-      case 4: ADP_DLAUNCH((score_batch_kernel<4, true>), a);
-      case 2: ADP_DLAUNCH((score_batch_kernel<2, true>), a);
-      default: ADP_DLAUNCH((score_batch_kernel<1, true>), a);
+      case 4: ADP_DLAUNCH((score_batch_kernel<false, 4, true>), a);
+      case 2: ADP_DLAUNCH((score_batch_kernel<false, 2, true>), a);
+      default: ADP_DLAUNCH((score_batch_kernel<false, 1, true>), a);
     }
   }
   switch (p.group) {
-    case 4: ADP_DLAUNCH((score_batch_kernel<4, false>), a);
-    case 2: ADP_DLAUNCH((score_batch_kernel<2, false>), a);
-    default: ADP_DLAUNCH((score_batch_kernel<1, false>), a);
+    case 4: ADP_DLAUNCH((score_batch_kernel<false, 4, false>), a);
+    case 2: ADP_DLAUNCH((score_batch_kernel<false, 2, false>), a);
+    default: ADP_DLAUNCH((score_batch_kernel<false, 1, false>), a);
   }
 }
 
-cudaError_t launch_mc(const McArgs& a, const LaunchPlan& p, cudaStream_t stream) {
+cudaError_t launch_mc(const McArgs& a, const LaunchPlan& p, bool fast, cudaStream_t stream) {
+  if (fast) {
+    if (p.mats_in_smem) ADP_DLAUNCH((mc_kernel<true, 1, true>), a);
+    ADP_DLAUNCH((mc_kernel<true, 1, false>), a);
+  }
   if (p.mats_in_smem) {
     switch (p.group) {
-      case 4: ADP_DLAUNCH((mc_kernel<4, true>), a);
-      case 2: ADP_DLAUNCH((mc_kernel<2, true>), a);
-      default: ADP_DLAUNCH((mc_kernel<1, true>), a);
+      case 4: ADP_DLAUNCH((mc_kernel<false, 4, true>), a);
+      case 2: ADP_DLAUNCH((mc_kernel<false, 2, true>), a);
+      default: ADP_DLAUNCH((mc_kernel<false, 1, true>), a);
     }
   }
   switch (p.group) {
-    case 4: ADP_DLAUNCH((mc_kernel<4, false>), a);
-    case 2: ADP_DLAUNCH((mc_kernel<2, false>), a);
-    default: ADP_DLAUNCH((mc_kernel<1, false>), a);
+    case 4: ADP_DLAUNCH((mc_kernel<false, 4, false>), a);
+    case 2: ADP_DLAUNCH((mc_kernel<false, 2, false>), a);
+    default: ADP_DLAUNCH((mc_kernel<false, 1, false>), a);
   }
 }
 

@@ -13,6 +13,8 @@ struct ScoreBatchArgs {
   double* terms;             // NULL or [B * n_ctx * n_terms]
   double* gmats;
   size_t gmat_stride;
+  int* redo;                 // [B + 1]: designs the fast kernel declined (letters outside ACGU/T); last = their count
+  int only_redo;             // general kernel: score only the flagged designs
 };
 
 struct McArgs {
@@ -34,8 +36,9 @@ struct McArgs {
   size_t gmat_stride;
 };
 
-LaunchPlan plan_design(const DeviceInfo&, int n_max, int jobs);
-cudaError_t launch_score(const ScoreBatchArgs&, const LaunchPlan&, cudaStream_t);
-cudaError_t launch_mc(const McArgs&, const LaunchPlan&, cudaStream_t);
+// fast = fold with pf_fast.cuh; plan.threads == 0 when n_max is outside its range
+LaunchPlan plan_design(const DeviceInfo&, int n_max, int jobs, bool fast);
+cudaError_t launch_score(const ScoreBatchArgs&, const LaunchPlan&, bool fast, cudaStream_t);
+cudaError_t launch_mc(const McArgs&, const LaunchPlan&, bool fast, cudaStream_t);
 
 }  // namespace adp

@@ -59,7 +59,8 @@ struct adp_engine {
   uint64_t launches = 0;
   // staging / scratch, grown on demand
   DevBuf b_seqs, b_ctxseqs, b_dg, b_bppm, b_qi, b_qj, b_qprobs, b_csts, b_motif, b_gmats, b_e, b_structs;
-  DevBuf b_score, b_terms, b_prob, b_mc[8], b_probe;
+  DevBuf b_score, b_terms, b_prob, b_mc[8], b_probe, b_redo, b_gmats2;
+  bool force_general = false;   // tests: route everything through the general kernels
   struct PendingCopy { void* dst; const void* src; size_t bytes; };
   std::vector<PendingCopy> pending;
 };
@@ -215,7 +216,7 @@ void adp_engine_destroy(adp_engine* e) {
   cudaSetDevice(e->device);
   if (e->own_stream) { cudaStreamSynchronize(e->own_stream); }
   DevBuf* bufs[] = {&e->b_seqs, &e->b_ctxseqs, &e->b_dg, &e->b_bppm, &e->b_qi, &e->b_qj, &e->b_qprobs, &e->b_csts, &e->b_motif,
-                    &e->b_gmats, &e->b_e, &e->b_structs, &e->b_score, &e->b_terms, &e->b_prob, &e->b_probe};
+                    &e->b_gmats, &e->b_e, &e->b_structs, &e->b_score, &e->b_terms, &e->b_prob, &e->b_probe, &e->b_redo, &e->b_gmats2};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : e->b_mc) b.release();
   if (e->d_pf) cudaFree(e->d_pf);
@@ -232,6 +233,7 @@ int adp_engine_set_stream(adp_engine* e, void* s) {
   return ADP_OK;
 }
 int adp_engine_set_async(adp_engine* e, int a) { if (!e) return ADP_ERR_ARG; e->async = a != 0; return ADP_OK; }
+int adp_engine_set_general_only(adp_engine* e, int on) { if (!e) return ADP_ERR_ARG; e->force_general = on != 0; return ADP_OK; }
 int adp_engine_sync(adp_engine* e) {
   if (!e) return ADP_ERR_ARG;
   ADP_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -289,10 +291,26 @@ static int run_pf(adp_engine* e, int B, int n, const uint8_t* d_seqs, int V, con
   for (int v = 0; v < V; v++) { a.variants[v] = variants[v]; any_outside |= variants[v].outside != 0; }
   a.csts = d_csts; a.motif = d_motif; a.T = e->d_pf;
   a.dG = d_dG; a.bppm = d_bppm; a.n_query = n_query; a.qi = d_qi; a.qj = d_qj; a.qprobs = d_qprobs;
-  LaunchPlan p = plan_pf(e->info, n, B * V, any_outside);
+  const int jobs = B * V;
+  LaunchPlan pfast = plan_pf_fast(e->info, n, jobs);
+  if (pfast.threads && !e->force_general) {
+    // fast kernel first; it flags the jobs it declines (letters outside ACGU/T), which the general kernel then folds
+    ADP_CUDA(e, e->b_redo.ensure((size_t)(jobs + 1) * sizeof(int)));
+    ADP_CUDA(e, cudaMemsetAsync(e->b_redo.p, 0, (size_t)(jobs + 1) * sizeof(int), e->stream));
+    a.redo = (int*)e->b_redo.p;
+    if (!pfast.mats_in_smem) {
+      ADP_CUDA(e, e->b_gmats.ensure((size_t)pfast.grid * pfast.gmat_stride * sizeof(double)));
+      a.gmats = (double*)e->b_gmats.p;
+      a.gmat_stride = pfast.gmat_stride;
+    }
+    ADP_CUDA(e, launch_pf_fast(a, pfast, e->stream));
+    e->launches++;
+    a.only_redo = 1;
+  }
+  LaunchPlan p = plan_pf(e->info, n, jobs, any_outside);
   if (!p.mats_in_smem) {
-    ADP_CUDA(e, e->b_gmats.ensure((size_t)p.grid * p.gmat_stride * sizeof(double)));
-    a.gmats = (double*)e->b_gmats.p;
+    ADP_CUDA(e, e->b_gmats2.ensure((size_t)p.grid * p.gmat_stride * sizeof(double)));
+    a.gmats = (double*)e->b_gmats2.p;
     a.gmat_stride = p.gmat_stride;
   }
   ADP_CUDA(e, launch_pf(a, p, e->stream));

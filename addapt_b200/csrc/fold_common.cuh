@@ -29,6 +29,7 @@ template <int G>
 struct CtaExec {
   static constexpr int kGroup = G;
   static constexpr int kWarp = 32;
+  static constexpr bool kSerial = false;
   __device__ __forceinline__ int tid() const { return threadIdx.x; }
   __device__ __forceinline__ int nthreads() const { return blockDim.x; }
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
@@ -60,6 +61,13 @@ struct CtaExec {
     return m ? __ffs(m) - 1 : -1;
   }
   __device__ __forceinline__ int warp_bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  // reduction over an aligned group of `g` lanes (g = power of two <= 32, uniform over the warp)
+  __device__ __forceinline__ double group_sum_rt(double v, int g) const {
+    for (int o = g >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ __forceinline__ int atomic_inc(int* ctr) const { return atomicAdd(ctr, 1); }
+  __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
 };
 #endif
 
@@ -68,6 +76,7 @@ struct CtaExec {
 struct SerialExec {
   static constexpr int kGroup = 1;
   static constexpr int kWarp = 1;
+  static constexpr bool kSerial = true;
   int tid() const { return 0; }
   int nthreads() const { return 1; }
   int lane() const { return 0; }
@@ -79,6 +88,9 @@ struct SerialExec {
   int warp_min(int v) const { return v; }
   int warp_first(bool flag) const { return flag ? 0 : -1; }
   int warp_bcast(int v, int) const { return v; }
+  double group_sum_rt(double v, int) const { return v; }
+  int atomic_inc(int* ctr) const { return (*ctr)++; }
+  void warp_sync() const {}
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -186,6 +198,37 @@ ADP_HD void load_context(const E& ex, SeqCtx& c, const uint8_t* seq, const Const
     }
   }
   ex.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// carving a raw (shared-memory) buffer into the per-construct arrays
+struct Carver {
+  char* p;
+  ADP_HD explicit Carver(void* base) : p((char*)base) {}
+  template <class T>
+  ADP_HD T* take(size_t count) {
+    size_t a = (size_t)p;
+    a = (a + 15) & ~(size_t)15;
+    T* r = (T*)a;
+    p = (char*)a + count * sizeof(T);
+    return r;
+  }
+};
+
+// bytes of the per-construct context arrays
+ADP_HD size_t ctx_bytes(int n) {
+  return 16 * 8 + (size_t)(n + 4) * (1 + 1 + 1) + (size_t)(n + 4) * 2 * 4;
+}
+
+ADP_HD void carve_ctx(Carver& cv, SeqCtx& c, int n) {
+  c.n = n;
+  c.S = cv.take<uint8_t>(n + 4);
+  c.flag = cv.take<uint8_t>(n + 4);
+  c.motif_at = cv.take<uint8_t>(n + 4);
+  c.partner = cv.take<uint16_t>(n + 4);
+  c.enc = cv.take<uint16_t>(n + 4);
+  c.upr = cv.take<uint16_t>(n + 4);
+  c.upl = cv.take<uint16_t>(n + 4);
 }
 
 ADP_HD bool is_motif_site(const SeqCtx& c, int i, int j) { return c.motif_len > 0 && (j - i + 1) == c.motif_len && c.motif_at[i]; }
@@ -296,7 +339,8 @@ ADP_HD void stage_small(const E& ex, PfSmall* dst, const PfTables* T) {
 }
 
 // unscaled hairpin weight (the caller multiplies by scale[u+2] and by the motif factor)
-ADP_HD double hairpin_x(const PfSmall& P, const PfTables* G, const uint8_t* S, int i, int j, int type) {
+template <class Tab>
+ADP_HD double hairpin_x(const Tab& P, const PfTables* G, const uint8_t* S, int i, int j, int type) {
   const int u = j - i - 1;
   const double q = u <= 30 ? P.hairpin[u] : G->hairpin[u];
   if (u == 3 || u == 4 || u == 6) {
@@ -313,7 +357,8 @@ ADP_HD double hairpin_x(const PfSmall& P, const PfTables* G, const uint8_t* S, i
   return q * P.mmH[type][S[i + 1]][S[j - 1]];
 }
 
-ADP_HD double interior_x(const PfSmall& P, const PfTables* G, int u1, int u2, int type, int type2, int si1, int sj1, int sp1, int sq1) {
+template <class Tab>
+ADP_HD double interior_x(const Tab& P, const PfTables* G, int u1, int u2, int type, int type2, int si1, int sj1, int sp1, int sq1) {
   const int big = u1 > u2 ? u1 : u2, small = u1 > u2 ? u2 : u1;
   if (big == 0) return P.stack[type][type2];
   if (small == 0) {
@@ -333,7 +378,8 @@ ADP_HD double interior_x(const PfSmall& P, const PfTables* G, int u1, int u2, in
   return P.interior[u1 + u2] * P.mmI[type][si1][sj1] * P.mmI[type2][sq1][sp1] * P.ninio[big - small];
 }
 
-ADP_HD double stem_x(const PfSmall& P, int type, bool have5, int s5, bool have3, int s3, bool ext) {
+template <class Tab>
+ADP_HD double stem_x(const Tab& P, int type, bool have5, int s5, bool have3, int s3, bool ext) {
   double e = 1.;
   if (have5 && have3) e = ext ? P.mmExt[type][s5][s3] : P.mmM[type][s5][s3];
   else if (have5) e = P.dangle5[type][s5];

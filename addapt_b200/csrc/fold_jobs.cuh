@@ -4,37 +4,9 @@
 #pragma once
 #include "mfe_core.cuh"
 #include "pf_core.cuh"
+#include "pf_fast.cuh"
 
 namespace adp {
-
-struct Carver {
-  char* p;
-  ADP_HD explicit Carver(void* base) : p((char*)base) {}
-  template <class T>
-  ADP_HD T* take(size_t count) {
-    size_t a = (size_t)p;
-    a = (a + 15) & ~(size_t)15;
-    T* r = (T*)a;
-    p = (char*)a + count * sizeof(T);
-    return r;
-  }
-};
-
-// bytes of the per-construct context arrays
-ADP_HD size_t ctx_bytes(int n) {
-  return 16 * 8 + (size_t)(n + 4) * (1 + 1 + 1) + (size_t)(n + 4) * 2 * 4;
-}
-
-ADP_HD void carve_ctx(Carver& cv, SeqCtx& c, int n) {
-  c.n = n;
-  c.S = cv.take<uint8_t>(n + 4);
-  c.flag = cv.take<uint8_t>(n + 4);
-  c.motif_at = cv.take<uint8_t>(n + 4);
-  c.partner = cv.take<uint16_t>(n + 4);
-  c.enc = cv.take<uint16_t>(n + 4);
-  c.upr = cv.take<uint16_t>(n + 4);
-  c.upl = cv.take<uint16_t>(n + 4);
-}
 
 // ---------------------------------------------------------------------------------------------------
 struct PfJob {
@@ -107,6 +79,61 @@ ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats)
     if (a > b) { const int t = a; a = b; b = t; }
     job.qprobs[q] = (a != b && a >= 0 && b < n) ? w.pr[tri(a + 1, b + 1)] : 0.;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The fast path (pf_fast.cuh) for the same job.  `small`: fast_small_bytes(n) of shared memory; `mats`:
+// fast_matrix_doubles(n) doubles (shared or global); `dstate`: host emulation only.  Returns false (on every
+// thread, nothing written) when the sequence holds a letter outside ACGU/T -- the caller then uses run_pf_job.
+template <class E>
+ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* mats, double* dstate = nullptr) {
+  const int n = job.n;
+  Carver cv(small);
+  PfHot* H = cv.take<PfHot>(1);
+  SeqCtx c;
+  carve_ctx(cv, c, n);
+  FastWork w;
+  w.ld = fast_ld(n);
+  w.R = fast_R(n);
+  w.vbase = cv.take<double>((size_t)kFastVectors * w.ld);
+  w.cn = cv.take<uint8_t>(w.ld);
+  w.cp = cv.take<uint8_t>(w.ld);
+  w.cells = cv.take<uint16_t>(w.ld);
+  w.counter = cv.take<int>(4);
+  w.qb = mats;
+  w.qm = mats + t4_count(n) + 1;
+  w.scaleG = job.T->scale;
+  w.dstate = dstate;
+  c.has_cst = job.cst != nullptr;
+  c.motif_len = job.motif ? job.motif->len : 0;
+  const double mboltz = job.motif ? job.motif->boltz : 1.;
+  if (ex.tid() == 0) w.counter[1] = 0;
+  stage_hot(ex, H, job.T);
+  for (int k = ex.tid(); k < w.ld; k += ex.nthreads()) w.vecp(10)[k] = job.T->eMLb[k];
+  load_context(ex, c, job.seq, job.cst, job.motif);   // ends with a barrier
+  if (!fast_codes(ex, c, w)) w.counter[1] = 1;
+  ex.sync();
+  if (w.counter[1]) return false;
+
+  const double Z = fast_inside(ex, c, *H, job.T, mboltz, w);
+  if (ex.tid() == 0)
+    *job.dG = Z > 0. ? (-log(Z) - n * log(job.T->pf_scale)) * job.T->kT / 1000. : (double)INFINITY;
+  if (!job.outside) return true;
+  FastOut out;
+  out.bppm = job.bppm;
+  out.n_query = job.n_query;
+  out.qi = job.qi;
+  out.qj = job.qj;
+  out.qprobs = job.qprobs;
+  if (Z > 0.) {
+    fast_outside(ex, c, *H, job.T, job.motif, mboltz, w, out);
+  } else {
+    if (job.bppm)
+      for (size_t k = ex.tid(); k < (size_t)n * (n + 1) / 2; k += ex.nthreads()) job.bppm[k] = 0.;
+    for (int q = ex.tid(); q < job.n_query; q += ex.nthreads()) job.qprobs[q] = 0.;
+    ex.sync();
+  }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(512) pf_batch_kernel(const PfBatchArgs a) {
   } else {
     mats = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
   }
+  if (a.only_redo && a.redo[jobs] == 0) return;
   for (int jid = blockIdx.x; jid < jobs; jid += gridDim.x) {
+    if (a.only_redo && !a.redo[jid]) continue;
     const int b = jid / a.V, v = jid - b * a.V;
     const VariantDev var = a.variants[v];
     PfJob job;
@@ -66,6 +68,50 @@ __global__ void __launch_bounds__(512) mfe_batch_kernel(const MfeBatchArgs a) {
     job.structure = a.structs ? a.structs + (size_t)b * n : nullptr;
     run_mfe_job(ex, job, small, mats);
     __syncthreads();
+  }
+}
+
+__device__ __forceinline__ PfJob make_pf_job(const PfBatchArgs& a, int jid) {
+  const int n = a.n;
+  const size_t ntri = (size_t)n * (n + 1) / 2;
+  const int b = jid / a.V, v = jid - b * a.V;
+  const VariantDev var = a.variants[v];
+  PfJob job;
+  job.seq = a.seqs + (size_t)b * n;
+  job.n = n;
+  job.cst = var.cst_id >= 0 ? a.csts + var.cst_id : nullptr;
+  job.motif = var.use_motif ? a.motif : nullptr;
+  job.T = a.T;
+  job.outside = var.outside != 0;
+  job.dG = a.dG + jid;
+  job.bppm = (a.bppm && job.outside) ? a.bppm + (size_t)jid * ntri : nullptr;
+  job.n_query = job.outside ? a.n_query : 0;
+  job.qi = a.qi;
+  job.qj = a.qj;
+  job.qprobs = a.qprobs ? a.qprobs + (size_t)jid * a.n_query : nullptr;
+  return job;
+}
+
+// Fast path: one construct per CTA, level sums of the generic interior loops in registers (pf_fast.cuh).
+// kThreads = 256 serves n <= 128 with two CTAs per SM at 100 nt; 512 serves n <= 256.
+template <int kThreads, bool kSmemMats>
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) pf_fast_kernel(const PfBatchArgs a) {
+  CtaExec<1> ex;
+  const int n = a.n;
+  const int jobs = a.B * a.V;
+  void* small = adp_smem;
+  double* mats;
+  if (kSmemMats) {
+    size_t off = (fast_small_bytes(n) + 15) & ~(size_t)15;
+    mats = reinterpret_cast<double*>(adp_smem + off);
+  } else {
+    mats = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
+  }
+  for (int jid = blockIdx.x; jid < jobs; jid += gridDim.x) {
+    const PfJob job = make_pf_job(a, jid);
+    const bool done = run_pf_job_fast(ex, job, small, mats);
+    if (!done && threadIdx.x == 0) { a.redo[jid] = 1; atomicAdd(a.redo + jobs, 1); }
+    __syncthreads();   // the next job reuses the working set
   }
 }
 
@@ -148,6 +194,36 @@ cudaError_t launch_pf(const PfBatchArgs& a, const LaunchPlan& p, cudaStream_t st
     case 2: ADP_LAUNCH((pf_batch_kernel<2, false>), a);
     default: ADP_LAUNCH((pf_batch_kernel<1, false>), a);
   }
+}
+
+LaunchPlan plan_pf_fast(const DeviceInfo& d, int n, int jobs) {
+  LaunchPlan p{};
+  p.threads = n <= fast_max_len(256) ? 256 : n <= fast_max_len(512) ? 512 : 0;
+  if (!p.threads) return p;
+  p.group = 1;
+  const size_t small_al = (fast_small_bytes(n) + 15) & ~(size_t)15;
+  const size_t mats_bytes = fast_matrix_doubles(n) * sizeof(double);
+  p.mats_in_smem = small_al + mats_bytes <= d.smem_optin;
+  p.smem_bytes = p.mats_in_smem ? small_al + mats_bytes : small_al;
+  p.gmat_stride = p.mats_in_smem ? 0 : fast_matrix_doubles(n);
+  size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);   // 1 KB reserved per resident CTA
+  size_t by_threads = p.threads == 256 ? 2 : 1;            // __launch_bounds__ of pf_fast_kernel
+  size_t occ = per_sm < by_threads ? per_sm : by_threads;
+  if (occ < 1) occ = 1;
+  long grid = (long)d.sm_count * (long)occ;
+  if (grid > jobs) grid = jobs;
+  if (grid < 1) grid = 1;
+  p.grid = (int)grid;
+  return p;
+}
+
+cudaError_t launch_pf_fast(const PfBatchArgs& a, const LaunchPlan& p, cudaStream_t stream) {
+  if (p.threads == 256) {
+    if (p.mats_in_smem) ADP_LAUNCH((pf_fast_kernel<256, true>), a);
+    ADP_LAUNCH((pf_fast_kernel<256, false>), a);
+  }
+  if (p.mats_in_smem) ADP_LAUNCH((pf_fast_kernel<512, true>), a);
+  ADP_LAUNCH((pf_fast_kernel<512, false>), a);
 }
 
 cudaError_t launch_mfe(const MfeBatchArgs& a, const LaunchPlan& p, cudaStream_t stream) {

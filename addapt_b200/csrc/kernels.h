@@ -25,6 +25,8 @@ struct PfBatchArgs {
   double* qprobs;              // [B*V*n_query]
   double* gmats;               // global scratch for the matrices when they do not fit in shared memory
   size_t gmat_stride;          // doubles per CTA
+  int* redo;                   // [B*V + 1] or NULL: jobs the fast kernel declined (non-ACGU letters); last = their count
+  int only_redo;               // general kernel: fold only the jobs flagged in `redo`
 };
 
 struct MfeBatchArgs {
@@ -53,6 +55,9 @@ struct DeviceInfo {
 };
 
 LaunchPlan plan_pf(const DeviceInfo&, int n, int jobs, bool any_outside);
+// fast path (pf_fast.cuh); plan.threads == 0 when the length is outside its range
+LaunchPlan plan_pf_fast(const DeviceInfo&, int n, int jobs);
+cudaError_t launch_pf_fast(const PfBatchArgs&, const LaunchPlan&, cudaStream_t);
 LaunchPlan plan_mfe(const DeviceInfo&, int n, int jobs);
 cudaError_t launch_pf(const PfBatchArgs&, const LaunchPlan&, cudaStream_t);
 cudaError_t launch_mfe(const MfeBatchArgs&, const LaunchPlan&, cudaStream_t);

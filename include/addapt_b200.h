@@ -47,6 +47,9 @@ const char *adp_last_error(const adp_engine *);          /* engine may be NULL: 
 int adp_engine_set_stream(adp_engine *, void *cuda_stream); /* cudaStream_t to launch on (default: own stream) */
 int adp_engine_set_async(adp_engine *, int async);       /* 1: do not synchronise before returning (device buffers only) */
 int adp_engine_sync(adp_engine *);
+/* 1: fold everything with the general kernels (any letters, any length <= ADP_MAX_LEN) instead of the fast
+ * ACGU-only kernels; results agree to rounding.  For parity tests of the general path. */
+int adp_engine_set_general_only(adp_engine *, int on);
 double adp_kT_kcal(const adp_engine *);                  /* fc->exp_params->kT/1000, reference scoring.cc:69,93 */
 int adp_device_count(void);
 uint64_t adp_launch_count(const adp_engine *);           /* kernels launched by this engine so far */

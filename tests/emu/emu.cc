@@ -4,6 +4,7 @@
 // single-thread SerialExec policy, so the recursions, constraint handling and traceback can be checked
 // against the oracle on a machine without a GPU (pytest -m "not gpu").  It exercises the same source the
 // sm_100a kernels are built from, but not their parallel decomposition -- that is what the -m gpu tests do.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +42,33 @@ int emu_eval(void* model, const char* seq, const char* db, int* e) {
 int emu_motif_contrib(void* model, const char* mseq, const char* mfold, double kd_uM, int* c) {
   auto* M = (EnergyModel*)model;
   try { *c = M->make_motif(mseq, mfold, M->kT_kcal() * std::log(kd_uM / 1e6)).contrib_dcal; return 0; } catch (std::string& er) { g_err = er; return -1; }
+}
+
+// `fast` = 1: the fast path (pf_fast.cuh); returns 1 when it declines the sequence (letters outside ACGU/T)
+int emu_pf2(void* model, int n, const char* seq, const char* cst, const char* mseq, const char* mfold, double kd_uM,
+            int outside, double* dG, double* bppm, int fast, int n_query, const int32_t* qi, const int32_t* qj, double* qprobs) {
+  auto* M = (EnergyModel*)model;
+  try {
+    ConstraintDev cd;
+    MotifDev md;
+    if (cst) build_constraint(cst, n, &cd);
+    if (mseq) md = M->make_motif(mseq, mfold, M->kT_kcal() * std::log(kd_uM / 1e6));
+    PfJob job{};
+    job.seq = (const uint8_t*)seq; job.n = n; job.cst = cst ? &cd : nullptr; job.motif = mseq ? &md : nullptr;
+    job.T = &M->pf(); job.outside = outside != 0; job.dG = dG; job.bppm = bppm;
+    job.n_query = outside ? n_query : 0; job.qi = qi; job.qj = qj; job.qprobs = qprobs;
+    SerialExec ex;
+    if (fast) {
+      std::vector<char> small(fast_small_bytes(n) + 64);
+      std::vector<double> mats(fast_matrix_doubles(n) + 2);
+      std::vector<double> dstate((size_t)2 * fast_R(n) * kFastLevels + 2);
+      return run_pf_job_fast(ex, job, small.data(), mats.data(), dstate.data()) ? 0 : 1;
+    }
+    std::vector<char> small(pf_small_bytes(n) + 64);
+    std::vector<double> mats(pf_matrix_doubles(n, job.outside) + 2);
+    run_pf_job(ex, job, small.data(), mats.data());
+    return 0;
+  } catch (std::string& er) { g_err = er; return -1; }
 }
 
 int emu_pf(void* model, int n, const char* seq, const char* cst, const char* mseq, const char* mfold, double kd_uM,
@@ -82,7 +110,7 @@ int emu_mfe(void* model, int n, const char* seq, const char* cst, const char* ms
 }
 
 // score of B sequences of one design problem (adp_problem layout of include/addapt_b200.h)
-int emu_score(void* model, const adp_problem* pr, int B, const char* seqs, double* score, double* terms) {
+int emu_score(void* model, const adp_problem* pr, int B, const char* seqs, double* score, double* terms, int fast) {
   auto* M = (EnergyModel*)model;
   try {
     CompiledProblem cp;
@@ -92,8 +120,9 @@ int emu_score(void* model, const adp_problem* pr, int B, const char* seqs, doubl
     cp.sp.csts = cp.csts.data();
     cp.sp.T = &M->pf();
     const int nm = cp.sp.n_max;
-    std::vector<char> small(pf_small_bytes(nm) + 64), extra(design_extra_bytes(nm) + 256);
-    std::vector<double> mats(pf_matrix_doubles(nm, false) + 2);
+    std::vector<char> small(std::max(pf_small_bytes(nm), fast_small_bytes(nm)) + 64), extra(design_extra_bytes(nm) + 256);
+    std::vector<double> mats(std::max(pf_matrix_doubles(nm, false), fast_matrix_doubles(nm)) + 2);
+    std::vector<double> dstate((size_t)2 * fast_R(nm) * kFastLevels + 2);
     Carver cv(extra.data());
     DesignScratch d;
     carve_design(cv, d, nm);
@@ -101,7 +130,10 @@ int emu_score(void* model, const adp_problem* pr, int B, const char* seqs, doubl
     const int nt = cp.sp.n_ctx * cp.sp.n_terms;
     for (int b = 0; b < B; b++) {
       std::memcpy(d.cur, seqs + (size_t)b * pr->n, pr->n);
-      score[b] = score_construct(ex, cp.sp, d.cur, d, small.data(), mats.data());
+      bool declined = false;
+      score[b] = fast ? score_construct<true>(ex, cp.sp, d.cur, d, small.data(), mats.data(), &declined, dstate.data())
+                      : score_construct<false>(ex, cp.sp, d.cur, d, small.data(), mats.data());
+      if (declined) { g_err = "fast path declined the sequence"; return 1; }
       if (terms) for (int t = 0; t < nt; t++) terms[(size_t)b * nt + t] = d.terms[t];
     }
     return 0;
@@ -109,7 +141,7 @@ int emu_score(void* model, const adp_problem* pr, int B, const char* seqs, doubl
 }
 
 int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, int n_steps, int kind, const double* targs,
-           char* final_seq, double* final_score, char* best_seq, double* best_score, int32_t* best_step, uint32_t* outcomes) {
+           char* final_seq, double* final_score, char* best_seq, double* best_score, int32_t* best_step, uint32_t* outcomes, int fast) {
   auto* M = (EnergyModel*)model;
   try {
     CompiledProblem cp;
@@ -121,8 +153,9 @@ int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, 
     std::vector<MoveTableDev> mv(1);
     compile_moves(*pr, &mv[0]);
     const int nm = cp.sp.n_max;
-    std::vector<char> small(pf_small_bytes(nm) + 64), extra(design_extra_bytes(nm) + 256);
-    std::vector<double> mats(pf_matrix_doubles(nm, false) + 2);
+    std::vector<char> small(std::max(pf_small_bytes(nm), fast_small_bytes(nm)) + 64), extra(design_extra_bytes(nm) + 256);
+    std::vector<double> mats(std::max(pf_matrix_doubles(nm, false), fast_matrix_doubles(nm)) + 2);
+    std::vector<double> dstate((size_t)2 * fast_R(nm) * kFastLevels + 2);
     Carver cv(extra.data());
     DesignScratch d;
     carve_design(cv, d, nm);
@@ -130,7 +163,8 @@ int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, 
     std::memcpy(d.cur, pr->init_seq, pr->n);
     McResult res;
     double ta[3] = {targs[0], kind == 1 ? targs[1] : 0., kind == 1 ? targs[2] : 1.};
-    mc_trajectory(ex, cp.sp, mv[0], seed, traj_id, n_steps, kind, ta, d, small.data(), mats.data(), &res);
+    if (fast) mc_trajectory<true>(ex, cp.sp, mv[0], seed, traj_id, n_steps, kind, ta, d, small.data(), mats.data(), &res, dstate.data());
+    else mc_trajectory<false>(ex, cp.sp, mv[0], seed, traj_id, n_steps, kind, ta, d, small.data(), mats.data(), &res);
     std::memcpy(final_seq, d.cur, pr->n);
     std::memcpy(best_seq, d.best, pr->n);
     *final_score = res.final_score; *best_score = res.best_score; *best_step = res.best_step;

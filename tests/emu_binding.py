@@ -21,12 +21,14 @@ class Emu:
         L.emu_motif_contrib.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_int)]
         L.emu_pf.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_int,
                              C.POINTER(C.c_double), C.c_void_p]
+        L.emu_pf2.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_int,
+                              C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_mfe.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double,
                               C.POINTER(C.c_int32), C.c_char_p]
-        L.emu_score.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_int, C.c_char_p, C.c_void_p, C.c_void_p]
+        L.emu_score.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_mc.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double),
                              C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int32),
-                             C.POINTER(C.c_uint32)]
+                             C.POINTER(C.c_uint32), C.c_int]
         self.model = L.emu_model_load(_b(par or DEFAULT_PAR))
         if not self.model:
             raise RuntimeError(L.emu_error().decode())
@@ -47,15 +49,25 @@ class Emu:
             raise self._err()
         return c.value
 
-    def pf(self, seq, cst=None, motif=None, bppm=False):
+    def pf(self, seq, cst=None, motif=None, bppm=False, fast=False, queries=None):
+        """fast=True runs pf_fast.cuh (raises NotImplementedError when it declines the sequence); queries = list of
+        0-based (i, j) pairs answered like adp_fold_eval_batch does (returned as a third value)."""
         n = len(seq)
         dg = C.c_double()
         bp = np.zeros(n * (n + 1) // 2)
-        rc = self.lib.emu_pf(self.model, n, _b(seq), _b(cst) if cst else None, _b(motif[0]) if motif else None,
-                             _b(motif[1]) if motif else None, motif[2] if motif else 0.0, 1 if bppm else 0, C.byref(dg),
-                             bp.ctypes.data)
+        nq = len(queries) if queries else 0
+        qi = np.array([q[0] for q in queries or []], dtype=np.int32)
+        qj = np.array([q[1] for q in queries or []], dtype=np.int32)
+        qp = np.full(max(nq, 1), -1.0)
+        rc = self.lib.emu_pf2(self.model, n, _b(seq), _b(cst) if cst else None, _b(motif[0]) if motif else None,
+                              _b(motif[1]) if motif else None, motif[2] if motif else 0.0, 1 if bppm else 0, C.byref(dg),
+                              bp.ctypes.data, 1 if fast else 0, nq, qi.ctypes.data, qj.ctypes.data, qp.ctypes.data)
+        if rc == 1:
+            raise NotImplementedError("fast path declined the sequence")
         if rc:
             raise self._err()
+        if queries is not None:
+            return dg.value, bp, qp[:nq]
         return (dg.value, bp) if bppm else dg.value
 
     def mfe(self, seq, cst=None, motif=None):
@@ -68,16 +80,16 @@ class Emu:
             raise self._err()
         return e.value, st.raw[:n].decode()
 
-    def score(self, problem: Problem, seqs, want_terms=False):
+    def score(self, problem: Problem, seqs, want_terms=False, fast=False):
         B = len(seqs)
         flat = b"".join(_b(s) for s in seqs)
         out = np.zeros(B)
         terms = np.zeros((B, problem.n_term_values))
-        if self.lib.emu_score(self.model, C.byref(problem.c), B, flat, out.ctypes.data, terms.ctypes.data):
+        if self.lib.emu_score(self.model, C.byref(problem.c), B, flat, out.ctypes.data, terms.ctypes.data, 1 if fast else 0):
             raise self._err()
         return (out, terms) if want_terms else out
 
-    def mc_run(self, problem: Problem, seed, traj_id, n_steps, thermostat=("annealing", 5.0, 0.0, 300)):
+    def mc_run(self, problem: Problem, seed, traj_id, n_steps, thermostat=("annealing", 5.0, 0.0, 300), fast=False):
         n = problem.n
         if thermostat[0] == "fixed":
             kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
@@ -87,7 +99,7 @@ class Emu:
         fsc, bsc, bst = C.c_double(), C.c_double(), C.c_int32()
         oc = (C.c_uint32 * 4)()
         if self.lib.emu_mc(self.model, C.byref(problem.c), seed, traj_id, n_steps, kind, ta, fs, C.byref(fsc), bs, C.byref(bsc),
-                           C.byref(bst), oc):
+                           C.byref(bst), oc, 1 if fast else 0):
             raise self._err()
         return dict(final_seq=fs.raw[:n].decode(), final_score=fsc.value, best_seq=bs.raw[:n].decode(), best_score=bsc.value,
                     best_step=bst.value, outcomes=list(oc))

@@ -22,6 +22,16 @@ def check_fold(oracle, emu, s, cst=None, motif=None):
         assert d1 == pytest.approx(d0, rel=DG_RTOL, abs=1e-12)
         np.testing.assert_allclose(b1, b0, rtol=BP_RTOL, atol=BP_ATOL)
     assert emu.mfe(s, cst=cst, motif=motif) == oracle.mfe(s, cst=cst, motif=motif)
+    if len(s) <= 256 and set(s.upper()) <= set("ACGUT"):
+        # the fast path (pf_fast.cuh: register-resident generic-loop levels, trimmed matrices, Qb overwritten by the
+        # outside pass) must describe the same ensemble
+        d2, b2 = emu.pf(s, cst=cst, motif=motif, bppm=True, fast=True)
+        if math.isinf(d0):
+            assert d2 == d0
+        else:
+            assert d2 == pytest.approx(d0, rel=DG_RTOL, abs=1e-12)
+            np.testing.assert_allclose(b2, b0, rtol=BP_RTOL, atol=BP_ATOL)
+            assert emu.pf(s, cst=cst, motif=motif, fast=True) == d2          # inside-only run
 
 
 def test_reference_sequences(oracle, emu):
@@ -61,6 +71,22 @@ def test_random_constraints_and_motif(oracle, emu):
         check_fold(oracle, emu, s, cst=cases.random_constraint(oracle, s, rng), motif=cases.THEO)
 
 
+def test_fast_path_queries_and_decline(oracle, emu):
+    s = cases.RHF6[:100].upper()
+    qs = [(0, 29), (47, 79), (79, 47), (50, 76), (54, 72), (5, 5), (3, 200), (10, 12)]
+    d, b, q = emu.pf(s, motif=cases.THEO, bppm=True, fast=True, queries=qs)
+    d0, b0 = oracle.pf(s, motif=cases.THEO, bppm=True)
+    from addapt_b200.capi import tri_index
+    want = [b0[tri_index(100, i, j)] if i != j and max(i, j) < 100 else 0.0 for i, j in qs]
+    np.testing.assert_allclose(q, want, rtol=BP_RTOL, atol=BP_ATOL)
+    with pytest.raises(NotImplementedError):
+        emu.pf("ACGNACGUACGU", fast=True)
+    rng = np.random.Generator(np.random.PCG64(5))
+    for alphabet in ("GC", "GU", "AU"):                   # densest pairing: every level of the loop recursion is busy
+        for n in (31, 64, 100, 128):
+            check_fold(oracle, emu, "".join(alphabet[k] for k in rng.integers(0, 2, n)))
+
+
 def test_lowercase_and_T(oracle, emu):
     assert emu.pf("acgtgaaaacgt") == pytest.approx(oracle.pf(cases.HAIRPIN), rel=1e-12)
     assert emu.mfe("acgtgaaaacgt") == oracle.mfe(cases.HAIRPIN)
@@ -90,9 +116,10 @@ def test_score(oracle, emu):
     for float_dg in (False, True):
         pr = cases.rhf6_problem(float_dg=float_dg)
         s0, t0 = oracle.score_batch(pr.as_oracle_dict(), designs, float_dg=float_dg)
-        s1, t1 = emu.score(pr, designs, want_terms=True)
-        np.testing.assert_allclose(s1, s0, rtol=1e-4 if float_dg else SC_RTOL)
-        np.testing.assert_allclose(t1, t0, rtol=1e-4 if float_dg else SC_RTOL)
+        for fast in (False, True):
+            s1, t1 = emu.score(pr, designs, want_terms=True, fast=fast)
+            np.testing.assert_allclose(s1, s0, rtol=1e-4 if float_dg else SC_RTOL)
+            np.testing.assert_allclose(t1, t0, rtol=1e-4 if float_dg else SC_RTOL)
 
 
 def test_score_with_contexts(oracle, emu):
@@ -102,6 +129,9 @@ def test_score_with_contexts(oracle, emu):
     s1, t1 = emu.score(pr, designs, want_terms=True)
     np.testing.assert_allclose(s1, s0, rtol=SC_RTOL)
     np.testing.assert_allclose(t1, t0, rtol=SC_RTOL)
+    s2, t2 = emu.score(pr, designs, want_terms=True, fast=True)
+    np.testing.assert_allclose(s2, s0, rtol=SC_RTOL)
+    np.testing.assert_allclose(t2, t0, rtol=SC_RTOL)
     # the score is the SUM over contexts (reference src/scoring.cc:123-132, tests/test_scoring.cc:302-330)
     single = sum(emu.score(cases.rhf6_problem(contexts=[c]), designs) for c in cases.SPACERS)
     np.testing.assert_allclose(s1, single, rtol=1e-12)
@@ -111,7 +141,8 @@ def test_monte_carlo_trajectory(oracle, emu):
     pr = cases.rhf6_problem()
     for seed, traj, thermo in ((2016, 7, ("annealing", 5.0, 0.0, 300)), (1, 123456789012, ("fixed", 1.0)), (3, 0, ("annealing", 2.0, 0.0, 7))):
         a = oracle.mc_run(pr.as_oracle_dict(), seed, traj, 30, thermostat=thermo)
-        b = emu.mc_run(pr, seed, traj, 30, thermostat=thermo)
+      for fast in (False, True):
+        b = emu.mc_run(pr, seed, traj, 30, thermostat=thermo, fast=fast)
         assert b["final_seq"] == a["final_seq"] and b["best_seq"] == a["best_seq"]
         assert b["outcomes"] == a["outcomes"] and b["best_step"] == a["best_step"]
         assert b["final_score"] == pytest.approx(a["final_score"], rel=SC_RTOL)

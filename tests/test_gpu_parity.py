@@ -104,6 +104,24 @@ def test_random_batches_by_length(oracle, engine, n):
     check_batch(oracle, engine, cases.random_seqs(6 if n > 150 else 24, n, 100 + n))
 
 
+def test_general_kernels_and_mixed_alphabet(oracle, engine):
+    """the fast pf kernels decline sequences with letters outside ACGU/T; the general kernel folds those (and, with
+    set_general_only, everything), and both agree with the oracle"""
+    seqs = cases.random_seqs(12, 90, 77)
+    mixed = list(seqs)
+    mixed[3] = mixed[3][:40] + "N" + mixed[3][41:]
+    mixed[8] = "N" * 5 + mixed[8][5:]
+    check_batch(oracle, engine, mixed)
+    check_batch(oracle, engine, mixed, motif=cases.THEO)
+    engine.set_general_only(1)
+    try:
+        check_batch(oracle, engine, seqs)
+        check_batch(oracle, engine, cases.templated_designs(8, 5, n=100), cst=cases.RHF6_ACTIVE[:100], motif=cases.THEO)
+        check_batch(oracle, engine, cases.random_seqs(4, 140, 78))
+    finally:
+        engine.set_general_only(0)
+
+
 def test_constraints_and_motif(oracle, engine):
     rng = np.random.Generator(np.random.PCG64(7))
     seqs = cases.templated_designs(16, 8, n=100)

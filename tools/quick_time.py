@@ -1,5 +1,5 @@
 import time, sys, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, '..')
 import addapt_b200
 from tests import cases
 eng = addapt_b200.Engine(0)
