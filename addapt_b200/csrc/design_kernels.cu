@@ -108,8 +108,16 @@ LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs, bool fast) {
     return cudaGetLastError();                                                                            \
   } while (0)
 
-cudaError_t launch_score(const ScoreBatchArgs& a, const LaunchPlan& p, bool fast, cudaStream_t stream) {
+static cudaError_t upload_fast_const(const PfTables* host_tables, cudaStream_t stream) {
+  FastConst fc;
+  fill_fast_const(&fc, host_tables);
+  return cudaMemcpyToSymbolAsync(c_fast_const, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
+}
+
+cudaError_t launch_score(const ScoreBatchArgs& a, const LaunchPlan& p, bool fast, const PfTables* host_tables, cudaStream_t stream) {
   if (fast) {
+    cudaError_t ce = upload_fast_const(host_tables, stream);
+    if (ce != cudaSuccess) return ce;
     if (p.mats_in_smem) ADP_DLAUNCH((score_batch_kernel<true, 1, true>), a);
     ADP_DLAUNCH((score_batch_kernel<true, 1, false>), a);
   }
@@ -127,8 +135,10 @@ cudaError_t launch_score(const ScoreBatchArgs& a, const LaunchPlan& p, bool fast
   }
 }
 
-cudaError_t launch_mc(const McArgs& a, const LaunchPlan& p, bool fast, cudaStream_t stream) {
+cudaError_t launch_mc(const McArgs& a, const LaunchPlan& p, bool fast, const PfTables* host_tables, cudaStream_t stream) {
   if (fast) {
+    cudaError_t ce = upload_fast_const(host_tables, stream);
+    if (ce != cudaSuccess) return ce;
     if (p.mats_in_smem) ADP_DLAUNCH((mc_kernel<true, 1, true>), a);
     ADP_DLAUNCH((mc_kernel<true, 1, false>), a);
   }

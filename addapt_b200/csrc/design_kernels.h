@@ -38,7 +38,8 @@ struct McArgs {
 
 // fast = fold with pf_fast.cuh; plan.threads == 0 when n_max is outside its range
 LaunchPlan plan_design(const DeviceInfo&, int n_max, int jobs, bool fast);
-cudaError_t launch_score(const ScoreBatchArgs&, const LaunchPlan&, bool fast, cudaStream_t);
-cudaError_t launch_mc(const McArgs&, const LaunchPlan&, bool fast, cudaStream_t);
+// host_tables: the engine's Boltzmann tables on the host (constant-bank factors of the fast kernels)
+cudaError_t launch_score(const ScoreBatchArgs&, const LaunchPlan&, bool fast, const PfTables* host_tables, cudaStream_t);
+cudaError_t launch_mc(const McArgs&, const LaunchPlan&, bool fast, const PfTables* host_tables, cudaStream_t);
 
 }  // namespace adp

@@ -303,7 +303,7 @@ static int run_pf(adp_engine* e, int B, int n, const uint8_t* d_seqs, int V, con
       a.gmats = (double*)e->b_gmats.p;
       a.gmat_stride = pfast.gmat_stride;
     }
-    ADP_CUDA(e, launch_pf_fast(a, pfast, e->stream));
+    ADP_CUDA(e, launch_pf_fast(a, pfast, &e->model.pf(), e->stream));
     e->launches++;
     a.only_redo = 1;
   }

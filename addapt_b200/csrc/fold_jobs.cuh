@@ -107,15 +107,15 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   c.has_cst = job.cst != nullptr;
   c.motif_len = job.motif ? job.motif->len : 0;
   const double mboltz = job.motif ? job.motif->boltz : 1.;
-  if (ex.tid() == 0) w.counter[1] = 0;
+  if (ex.tid() == 0) w.counter[2] = 0;
   stage_hot(ex, H, job.T);
   for (int k = ex.tid(); k < w.ld; k += ex.nthreads()) w.vecp(10)[k] = job.T->eMLb[k];
   load_context(ex, c, job.seq, job.cst, job.motif);   // ends with a barrier
-  if (!fast_codes(ex, c, w)) w.counter[1] = 1;
+  if (!fast_codes(ex, c, w)) w.counter[2] = 1;
   ex.sync();
-  if (w.counter[1]) return false;
+  if (w.counter[2]) return false;
 
-  const double Z = fast_inside(ex, c, *H, job.T, mboltz, w);
+  const double Z = c.has_cst ? fast_inside<true>(ex, c, *H, job.T, mboltz, w) : fast_inside<false>(ex, c, *H, job.T, mboltz, w);
   if (ex.tid() == 0)
     *job.dG = Z > 0. ? (-log(Z) - n * log(job.T->pf_scale)) * job.T->kT / 1000. : (double)INFINITY;
   if (!job.outside) return true;
@@ -126,7 +126,8 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   out.qj = job.qj;
   out.qprobs = job.qprobs;
   if (Z > 0.) {
-    fast_outside(ex, c, *H, job.T, job.motif, mboltz, w, out);
+    if (c.has_cst) fast_outside<true>(ex, c, *H, job.T, job.motif, mboltz, w, out);
+    else fast_outside<false>(ex, c, *H, job.T, job.motif, mboltz, w, out);
   } else {
     if (job.bppm)
       for (size_t k = ex.tid(); k < (size_t)n * (n + 1) / 2; k += ex.nthreads()) job.bppm[k] = 0.;

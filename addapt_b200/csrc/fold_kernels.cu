@@ -217,7 +217,11 @@ LaunchPlan plan_pf_fast(const DeviceInfo& d, int n, int jobs) {
   return p;
 }
 
-cudaError_t launch_pf_fast(const PfBatchArgs& a, const LaunchPlan& p, cudaStream_t stream) {
+cudaError_t launch_pf_fast(const PfBatchArgs& a, const LaunchPlan& p, const PfTables* host_tables, cudaStream_t stream) {
+  FastConst fc;
+  fill_fast_const(&fc, host_tables);
+  cudaError_t ce = cudaMemcpyToSymbolAsync(c_fast_const, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
+  if (ce != cudaSuccess) return ce;
   if (p.threads == 256) {
     if (p.mats_in_smem) ADP_LAUNCH((pf_fast_kernel<256, true>), a);
     ADP_LAUNCH((pf_fast_kernel<256, false>), a);

@@ -57,7 +57,8 @@ struct DeviceInfo {
 LaunchPlan plan_pf(const DeviceInfo&, int n, int jobs, bool any_outside);
 // fast path (pf_fast.cuh); plan.threads == 0 when the length is outside its range
 LaunchPlan plan_pf_fast(const DeviceInfo&, int n, int jobs);
-cudaError_t launch_pf_fast(const PfBatchArgs&, const LaunchPlan&, cudaStream_t);
+// host_tables: the engine's Boltzmann tables on the host (their size-indexed factors go to the constant bank)
+cudaError_t launch_pf_fast(const PfBatchArgs&, const LaunchPlan&, const PfTables* host_tables, cudaStream_t);
 LaunchPlan plan_mfe(const DeviceInfo&, int n, int jobs);
 cudaError_t launch_pf(const PfBatchArgs&, const LaunchPlan&, cudaStream_t);
 cudaError_t launch_mfe(const MfeBatchArgs&, const LaunchPlan&, cudaStream_t);

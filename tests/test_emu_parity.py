@@ -141,13 +141,13 @@ def test_monte_carlo_trajectory(oracle, emu):
     pr = cases.rhf6_problem()
     for seed, traj, thermo in ((2016, 7, ("annealing", 5.0, 0.0, 300)), (1, 123456789012, ("fixed", 1.0)), (3, 0, ("annealing", 2.0, 0.0, 7))):
         a = oracle.mc_run(pr.as_oracle_dict(), seed, traj, 30, thermostat=thermo)
-      for fast in (False, True):
-        b = emu.mc_run(pr, seed, traj, 30, thermostat=thermo, fast=fast)
-        assert b["final_seq"] == a["final_seq"] and b["best_seq"] == a["best_seq"]
-        assert b["outcomes"] == a["outcomes"] and b["best_step"] == a["best_step"]
-        assert b["final_score"] == pytest.approx(a["final_score"], rel=SC_RTOL)
-        assert b["best_score"] == pytest.approx(a["best_score"], rel=SC_RTOL)
-        assert sum(b["outcomes"]) == 30
+        for fast in (False, True):
+            b = emu.mc_run(pr, seed, traj, 30, thermostat=thermo, fast=fast)
+            assert b["final_seq"] == a["final_seq"] and b["best_seq"] == a["best_seq"]
+            assert b["outcomes"] == a["outcomes"] and b["best_step"] == a["best_step"]
+            assert b["final_score"] == pytest.approx(a["final_score"], rel=SC_RTOL)
+            assert b["best_score"] == pytest.approx(a["best_score"], rel=SC_RTOL)
+            assert sum(b["outcomes"]) == 30
 
 
 def test_move_table_errors(emu):
