@@ -21,7 +21,7 @@ $(LIB): build/engine.o build/fold_kernels.o build/design_kernels.o build/energy_
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -Xcompiler -static-libstdc++,-static-libgcc -Xlinker --exclude-libs,ALL
 
 host: $(LIB)
-	@if [ -f addapt_b200/host/Makefile ]; then $(MAKE) -C addapt_b200/host; fi
+	$(MAKE) -C addapt_b200/host
 oracle:
 	$(MAKE) -C oracle
 emu:
@@ -31,4 +31,5 @@ clean:
 	rm -rf build $(LIB)
 	$(MAKE) -C oracle clean
 	$(MAKE) -C tests/emu clean
+	$(MAKE) -C addapt_b200/host clean
 .PHONY: all host oracle emu clean

@@ -205,12 +205,13 @@ ADP_HD void load_context(const E& ex, SeqCtx& c, const uint8_t* seq, const Const
 struct Carver {
   char* p;
   ADP_HD explicit Carver(void* base) : p((char*)base) {}
+  // 16-byte aligned array of `count` T.  Only pointer arithmetic on `p` (no integer -> pointer cast), so that the
+  // compiler keeps the address space of the buffer (shared memory loads instead of generic ones).
   template <class T>
   ADP_HD T* take(size_t count) {
-    size_t a = (size_t)p;
-    a = (a + 15) & ~(size_t)15;
-    T* r = (T*)a;
-    p = (char*)a + count * sizeof(T);
+    p += (16 - ((size_t)p & 15)) & 15;
+    T* r = reinterpret_cast<T*>(p);
+    p += count * sizeof(T);
     return r;
   }
 };
