@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing of the design path: one process per GPU, trajectories (or sequences) sharded by id with NO traffic
+inside the loop; the only exchange is the final gather of each rank's top designs.
+
+In the reference, parallelism is N independent OS processes with different seeds whose TSV files are merged offline
+(reference data/20160705_production_run_favor_wt/production_run.sh:5-8, tools/utils.py:27-51).  Here trajectory t draws from
+Philox keyed by (seed, t), so any partition of the ids over ranks gives the same trajectories, and the merge is one
+all_gather of K fixed-size records per rank (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+import numpy as np
+
+
+def shard_range(n_units, rank, world):
+    """contiguous id range [lo, hi) of `rank`: sizes differ by at most one, union is [0, n_units)"""
+    base, extra = divmod(n_units, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def local_top_k(scores, k):
+    """indices of the k best (largest) scores, best first; ties broken by lower index so the result is deterministic"""
+    scores = np.asarray(scores, dtype=np.float64)
+    k = min(k, scores.shape[0])
+    order = np.lexsort((np.arange(scores.shape[0]), -scores))
+    return order[:k]
+
+
+def gather_top_designs(scores, seqs, ids, k, dist=None, device=None):
+    """Every rank passes its local trajectories' best scores [m], best sequences [m, n] (uint8) and global ids [m];
+    every rank gets the global top-k (scores [k], seqs [k, n], ids [k]), best first, identical on all ranks.
+    `dist` = torch.distributed (initialised) or None for a single process."""
+    scores = np.asarray(scores, dtype=np.float64)
+    seqs = np.asarray(seqs, dtype=np.uint8)
+    ids = np.asarray(ids, dtype=np.int64)
+    pick = local_top_k(scores, k)
+    loc_s, loc_q, loc_i = scores[pick], seqs[pick], ids[pick]
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return loc_s, loc_q, loc_i
+    import torch
+    world = dist.get_world_size()
+    n = seqs.shape[1]
+    kk = int(k)
+    # fixed-size record per rank: k scores (f64), k ids (i64 as f64 bit pattern is avoided: two tensors), k*n bytes; pad short ranks
+    pad = kk - loc_s.shape[0]
+    s_t = torch.full((kk,), -np.inf, dtype=torch.float64)
+    i_t = torch.full((kk,), -1, dtype=torch.int64)
+    q_t = torch.zeros((kk, n), dtype=torch.uint8)
+    s_t[:kk - pad] = torch.from_numpy(loc_s)
+    i_t[:kk - pad] = torch.from_numpy(loc_i)
+    q_t[:kk - pad] = torch.from_numpy(np.ascontiguousarray(loc_q))
+    if device is not None:
+        s_t, i_t, q_t = s_t.to(device), i_t.to(device), q_t.to(device)
+    S = [torch.empty_like(s_t) for _ in range(world)]
+    I = [torch.empty_like(i_t) for _ in range(world)]
+    Q = [torch.empty_like(q_t) for _ in range(world)]
+    dist.all_gather(S, s_t)
+    dist.all_gather(I, i_t)
+    dist.all_gather(Q, q_t)
+    all_s = torch.cat(S).cpu().numpy()
+    all_i = torch.cat(I).cpu().numpy()
+    all_q = torch.cat(Q).cpu().numpy()
+    valid = all_i >= 0
+    all_s, all_i, all_q = all_s[valid], all_i[valid], all_q[valid]
+    order = np.lexsort((all_i, -all_s))[:kk]          # best score first, ties by global id: independent of the sharding
+    return all_s[order], all_q[order], all_i[order]

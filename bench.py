@@ -332,7 +332,8 @@ def main():
         kernel_ms = ms_dev / args.steps                               # one kernel launch per step; events bracket only it
         achieved = terms_per_unit * units_per_step / (kernel_ms * 1e-3) / 1e9
         roofline = {"bound": "sm_fp64_issue", "achieved": achieved, "peak": peak, "unit": "GFMA/s", "frac": achieved / peak,
-                    "traffic": None, "terms_per_unit": terms_per_unit, "w_in": w_in, "w_out": w_out,
+                    "traffic": None, "traffic_note": "dram bytes of the kernel are ~1e-6 of HBM peak (profiles/: 0.7-0.8 MB read, 0 written per 4,096-design launch); the matrices never leave shared memory",
+                    "terms_per_unit": terms_per_unit, "w_in": w_in, "w_out": w_out,
                     "peak_source": "adp_measure_dfma_rate: register-resident DFMA loop on this GPU (MEASURED_PEAKS.json holds only HBM / bf16 peaks, which do not bound this path)",
                     "hbm_frac_of_measured": None}
         try:
@@ -362,6 +363,15 @@ def main():
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
+    if wl == "mc":
+        # the one exchange step of the design run: every rank's best designs, merged to a global top-K over NCCL
+        from addapt_b200.sharding import gather_top_designs
+        t0 = time.perf_counter()
+        top_s, top_q, top_i = gather_top_designs(d_best.cpu().numpy(), d_bseq.cpu().numpy(), np.arange(rank * mc_traj, (rank + 1) * mc_traj),
+                                                 min(1024, mc_traj), dist if world > 1 else None, dev)
+        if rank == 0:
+            print(json.dumps({"top_designs_gather": {"k": int(top_s.shape[0]), "ranks": world, "best_score": float(top_s[0]),
+                                                     "best_seq": bytes(top_q[0]).decode(), "seconds": time.perf_counter() - t0}}), file=sys.stderr)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
