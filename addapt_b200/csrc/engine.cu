@@ -61,6 +61,9 @@ struct adp_engine {
   DevBuf b_seqs, b_ctxseqs, b_dg, b_bppm, b_qi, b_qj, b_qprobs, b_csts, b_motif, b_gmats, b_e, b_structs;
   DevBuf b_score, b_terms, b_prob, b_mc[8], b_probe, b_redo, b_gmats2;
   bool force_general = false;   // tests: route everything through the general kernels
+  MotifDev h_motif{};           // last staged motif record (host copy) and its key
+  std::string motif_seq, motif_fold;
+  double motif_kd = 0.;
   struct PendingCopy { void* dst; const void* src; size_t bytes; };
   std::vector<PendingCopy> pending;
 };
@@ -121,20 +124,26 @@ int check_batch(adp_engine* e, int B, int n, const void* seqs) {
   return ADP_OK;
 }
 
-// uploads a motif record (or none) and returns its device pointer
+// uploads a motif record (or none) and returns its device pointer.  The record of the last call is cached, so a
+// loop that keeps folding with the same aptamer costs neither a table evaluation nor a host synchronisation.
 int stage_motif(adp_engine* e, const adp_motif* motif, const MotifDev** d_motif, MotifDev* host_copy = nullptr) {
   *d_motif = nullptr;
   if (!motif || !motif->seq) return ADP_OK;
   if (!motif->fold) return fail_arg(e, "aptamer without a fold");
-  MotifDev md;
-  try {
-    md = e->model.make_motif(motif->seq, motif->fold, e->model.kT_kcal() * std::log(motif->kd_uM / 1e6));
-  } catch (std::string& s) { return fail_arg(e, s); }
-  ADP_CUDA(e, e->b_motif.ensure(sizeof md));
-  ADP_CUDA(e, cudaMemcpyAsync(e->b_motif.p, &md, sizeof md, cudaMemcpyHostToDevice, e->stream));
-  ADP_CUDA(e, cudaStreamSynchronize(e->stream));   // md is a stack object
+  const bool cached = e->b_motif.p && e->motif_seq == motif->seq && e->motif_fold == motif->fold && e->motif_kd == motif->kd_uM;
+  if (!cached) {
+    try {
+      e->h_motif = e->model.make_motif(motif->seq, motif->fold, e->model.kT_kcal() * std::log(motif->kd_uM / 1e6));
+    } catch (std::string& s) { return fail_arg(e, s); }
+    ADP_CUDA(e, e->b_motif.ensure(sizeof(MotifDev)));
+    ADP_CUDA(e, cudaStreamSynchronize(e->stream));   // kernels of earlier calls may still read the old record
+    ADP_CUDA(e, cudaMemcpyAsync(e->b_motif.p, &e->h_motif, sizeof(MotifDev), cudaMemcpyHostToDevice, e->stream));
+    e->motif_seq = motif->seq;
+    e->motif_fold = motif->fold;
+    e->motif_kd = motif->kd_uM;
+  }
   *d_motif = (const MotifDev*)e->b_motif.p;
-  if (host_copy) *host_copy = md;
+  if (host_copy) *host_copy = e->h_motif;
   return ADP_OK;
 }
 

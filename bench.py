@@ -213,7 +213,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = addapt_b200.Engine(local)          # raises without the CUDA library / device: no fallback
-    stream = torch.cuda.current_stream()
+    # one explicit stream for torch (events, L2 flush) AND the engine's kernels: torch.cuda.Event only sees the stream it is
+    # recorded on, and the legacy default stream (handle 0) would make the engine fall back to its own stream
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     dev = torch.device("cuda", local)
     B, n = args.batch, args.n
