@@ -33,6 +33,9 @@ constexpr int kFastLevels = 14;       // level sums per thread: s = 4+par, 6+par
 
 struct PfHot {                        // shared memory, staged once per CTA
   double FI[256], F1n[256], FM[256];  // mismatch_interior, mismatch_interior_1n, multiloop stem factor (closing orientation)
+  // The matrices hold Qb (inside) / the outside weight PREMULTIPLIED by FI of the pair (inner orientation inside, outer
+  // orientation outside), so that the level recursion reads its candidates with one load.  Ratios for the other readers:
+  double RI[256], RB[256], R1[256], RM[256];   // 1/FI, terminal-AU factor / FI, F1n / FI, FM / FI  (0 for non-pairs)
   double tapB[32];                    // bulge[u] * scale[u+2]                      (u >= 2)
   double tap1n[32];                   // interior[u+1] * ninio[u-1] * scale[u+3]    (1 x u loop, u >= 3)
   double scale1, scale2, eMLb1, MLclosing, TermAU, pad;
@@ -70,6 +73,11 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
     H->FI[q] = t ? T->mmI[t][u][v] : 0.;
     H->F1n[q] = t ? T->mm1nI[t][u][v] : 0.;
     H->FM[q] = t ? T->mmM[rtype(t)][v][u] * (t > 2 ? T->TermAU : 1.) * T->MLintern : 0.;
+    const double inv = t ? 1. / T->mmI[t][u][v] : 0.;
+    H->RI[q] = inv;
+    H->RB[q] = t ? (t > 2 ? T->TermAU : 1.) * inv : 0.;
+    H->R1[q] = t ? T->mm1nI[t][u][v] * inv : 0.;
+    H->RM[q] = t ? H->FM[q] * inv : 0.;
   }
   for (int q = ex.tid(); q < 32; q += ex.nthreads()) {
     H->tapB[q] = (q >= 2 && q <= 30) ? T->bulge[q] * T->scale[q + 2] : 0.;
@@ -84,7 +92,7 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
 #endif
 }
 
-constexpr int kFastVectors = 18;
+constexpr int kFastVectors = 16;
 
 struct FastWork {
   double* qb;      // Qb, then (outside) the outside weights: trimmed triangle
@@ -202,6 +210,41 @@ ADP_HD bool fast_codes(const E& ex, const SeqCtx& c, FastWork& w) {
 #define ADP_LEVEL_ZERO()                                                                                  \
   d[0] = d[1] = d[2] = d[3] = d[4] = d[5] = d[6] = d[7] = d[8] = d[9] = d[10] = d[11] = d[12] = d[13] = 0.;
 
+// Partial sum (this lane's share) of  sum_{k=i+1}^{nr} (Qm(i,k-1) [k-i >= 5] + eMLb[k-i] [k-i <= run]) * Qm1(k,j)  -- the terms
+// that extend row i of Qm to the new column.  Lane `sub` of a group of G takes every G-th term.  Two plain loops
+// (unpaired prefix; earlier multiloop part walked along row i with a second-order offset increment).
+ADP_HD double qm_row_terms(const double* qm, const double* qm1, const double* eMLbS, int i, int nr, int run, int sub, int G) {
+  double s0 = 0., s1 = 0.;
+  {
+    int umax = nr - i;
+    if (umax > run) umax = run;
+    const double* pe = eMLbS + 1 + sub;
+    const double* pq = qm1 + i + 1 + sub;
+    int u = 1 + sub;
+    for (; u + G <= umax; u += 2 * G) {
+      s0 += pe[0] * pq[0];
+      s1 += pe[G] * pq[G];
+      pe += 2 * G;
+      pq += 2 * G;
+    }
+    if (u <= umax) s0 += pe[0] * pq[0];
+  }
+  {
+    int k = i + 5 + sub;
+    int off = t4(i, k - 1);
+    int step = G * (k - 5) + ((G * (G - 1)) >> 1);      // column k-1 -> k-1+G
+    const int step2 = G * G;
+    const double* pq = qm1 + k;
+    for (; k <= nr; k += G) {
+      s1 += qm[off] * pq[0];
+      off += step;
+      step += step2;
+      pq += G;
+    }
+  }
+  return s0 + s1;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // inside pass.  Returns Z = Q(1,n) (scaled) on every thread.
 // vector roles: 0/1 Qm1 columns by parity, 2 exterior terms of the listed cells, 3 xA (Qb * terminal factor, column
@@ -245,7 +288,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     const bool cuj = !kCst || can_unpair(c, jn);
     const bool cuj1 = !kCst || can_unpair(c, jn - 1);
     const int upl_j1 = kCst ? (int)c.upl[jn - 1] : 1000;
-    const double* xI_rd = w.vecp(6 + (jn % 3));       // column jn-3
+    const double* col3 = qb + (((jn - 7) * (jn - 8)) >> 1) - 2;   // Qb*FI(k, jn-3) = col3[k + 1]
     const double* qm1_prev = w.vecp((jn - 1) & 1);
     double* qm1_cur = w.vecp(jn & 1);
     int* counter = w.counter + (jn & 1);
@@ -263,11 +306,10 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         if (smax >= 4) {
           const int upr_i1 = kCst ? (int)c.upr[i + 1] : 1000;
           const bool g = upr_i1 >= 1 && cuj1;
-          const int cpA = cp[i + 3];
           const bool ok1 = upr_i1 >= 2, ok2 = upl_j1 >= 2;
-          const double* xi = xI_rd + i - 1;
+          const double* xi = col3 + i;                 // xi[S] = Qb*FI(i+S-1, jn-3)
           const int i2 = i + 2;
-#define ADP_B1 ((ok1 && upl_j1 >= S - 2) ? qb[(((jn - 3 - S) * (jn - 4 - S)) >> 1) + i2] * H.FI[(cn[jn + 1 - S] << 4) | cpA] : 0.)
+#define ADP_B1 ((ok1 && upl_j1 >= S - 2) ? qb[(((jn - 3 - S) * (jn - 4 - S)) >> 1) + i2] : 0.)
 #define ADP_B2 ((ok2 && upr_i1 >= S - 2) ? xi[S] : 0.)
           if (par) { ADP_LEVEL_PASS(1, ADP_B1, ADP_B2) } else { ADP_LEVEL_PASS(0, ADP_B1, ADP_B2) }
 #undef ADP_B1
@@ -329,7 +371,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               corner_u(q, &u1, &u2);
               if (u1 <= u1cap && u2 <= u2cap && u1 + u2 <= room) {
                 const int k = i + 1 + u1, l = j - 1 - u2;
-                const double v = qb[t4(k, l)];
+                const double v = qb[t4(k, l)] * H.RI[(cn[l] << 4) | cp[k]];
                 if (v != 0.)
                   other += v * w.scaleG[u1 + u2 + 2] * interior_x(*G, G, u1, u2, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1]);
               }
@@ -337,10 +379,10 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
             // bulges with the unpaired run on the 3' side: k = i+1, l = j-1-u2, u2 >= 2
             {
               const int hi = room < u2cap ? room : u2cap;
-              const int sk = c.S[i + 1];
+              const int cpk = cp[i + 1];
               for (int u2 = 2 + sub; u2 <= hi; u2 += Gs) {
                 const int l = j - 1 - u2;
-                accB += qb[t4(i + 1, l)] * au_factor(H, sk, c.S[l]) * H.tapB[u2];
+                accB += qb[t4(i + 1, l)] * H.RB[(cn[l] << 4) | cpk] * H.tapB[u2];
               }
             }
             // 1 x u2 loops: k = i+2, u2 >= 3
@@ -350,7 +392,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               const int cpk = cp[i + 2];
               for (int u2 = 3 + sub; u2 <= hi; u2 += Gs) {
                 const int l = j - 1 - u2;
-                acc1n += qb[t4(i + 2, l)] * H.F1n[(cn[l] << 4) | cpk] * H.tap1n[u2];
+                acc1n += qb[t4(i + 2, l)] * H.R1[(cn[l] << 4) | cpk] * H.tap1n[u2];
               }
             }
             // bulges with the run on the 5' side: l = j-1, k = i+1+u1, u1 >= 2 -- premultiplied column vector
@@ -371,16 +413,21 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
           {
             int k = i + 6 + sub;
             int off = t4(i + 1, k - 1);
+            int step = Gs * (k - 5) + ((Gs * (Gs - 1)) >> 1);     // column k-1 -> k-1+Gs
+            const int step2 = Gs * Gs;
+            const double* pq = qm1_prev + k;
             for (; k <= j - 5; k += Gs) {
-              accML += qm[off] * qm1_prev[k];
-              off += Gs * (k - 5) + ((Gs * (Gs - 1)) >> 1);       // column k-1 -> k-1+Gs
+              accML += qm[off] * pq[0];
+              off += step;
+              step += step2;
+              pq += Gs;
             }
           }
           acc = other + au_factor(H, si, sj) * accB + H.F1n[codeij] * acc1n + accML * (H.MLclosing * H.FM[codeij] * H.scale2);
         }
         acc = ex.group_sum_rt(acc, Gs);
         if (valid && sub == 0) {
-          qb[t4(i, j)] = acc;
+          qb[t4(i, j)] = (i > 1 && j < n) ? acc * H.FI[(cn[j] << 4) | cp[i]] : acc;     // stored premultiplied
           qm1_cur[i] += acc * fast_stem_ml(c, H, G, w, type, i, j);
           ext[slot] = acc * fast_stem_ext(c, G, type, i, j) * q1[i - 1];
         }
@@ -391,51 +438,25 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     //      lane group sums the same number of terms); exterior prefix; preparation of column j+1
     {
       double* x1n_wr = w.vecp(4 + (j & 1));
-      double* xI_wr = w.vecp(6 + (j % 3));
-      const int cnj = cn[j] << 4, sj = c.S[j];
+      const int cnj = cn[j] << 4;
       for (int r = tid; r < nr; r += nt) {
         const int i = r + 1;
-        const double v = qb[t4(i, j)];
+        const double v = qb[t4(i, j)];                  // Qb * FI; rows / columns at the sequence ends are never read back
         const int code = cnj | cp[i];
-        xA[i] = v * au_factor(H, c.S[i], sj);
-        x1n_wr[i] = v * H.F1n[code];
-        xI_wr[i] = v * H.FI[code];
+        xA[i] = v * H.RB[code];
+        x1n_wr[i] = v * H.R1[code];
       }
       const int npair = (nr + 1) >> 1;
       const int lg = group_lg(npair, nt_lg, warp_lg);
       const int Gc = 1 << lg, slotsC = nt >> lg, subC = tid & (Gc - 1);
-      const int gstep = (Gc * (Gc - 1)) >> 1;
       for (int slot0 = 0; slot0 < npair; slot0 += slotsC) {
         const int slot = slot0 + (tid >> lg);
         const bool valid = slot < npair;
         const int iA = slot + 1, iB = nr - slot;       // iA <= iB; equal for the middle row of an odd count
         double tA = 0., tB = 0.;
         if (valid) {
-          // row iA: k = iA+1 .. nr;   term (Qm(iA,k-1) [k-iA >= 5] + eMLb[k-iA] [run]) * Qm1(k,j)
-          {
-            const int run = kCst ? (int)c.upr[iA] : 1000;
-            int k = iA + 1 + subC;
-            int off = t4(iA, k - 1);                   // meaningful once k - iA >= 5
-            for (; k <= nr; k += Gc) {
-              const int u = k - iA;
-              double wgt = u >= 5 ? qm[off] : 0.;
-              if (u <= run) wgt += eMLbS[u];
-              tA += wgt * qm1_cur[k];
-              off += Gc * (k - 5) + gstep;
-            }
-          }
-          if (iB > iA) {
-            const int run = kCst ? (int)c.upr[iB] : 1000;
-            int k = iB + 1 + subC;
-            int off = t4(iB, k - 1);
-            for (; k <= nr; k += Gc) {
-              const int u = k - iB;
-              double wgt = u >= 5 ? qm[off] : 0.;
-              if (u <= run) wgt += eMLbS[u];
-              tB += wgt * qm1_cur[k];
-              off += Gc * (k - 5) + gstep;
-            }
-          }
+          tA = qm_row_terms(qm, qm1_cur, eMLbS, iA, nr, kCst ? (int)c.upr[iA] : 1000, subC, Gc);
+          if (iB > iA) tB = qm_row_terms(qm, qm1_cur, eMLbS, iB, nr, kCst ? (int)c.upr[iB] : 1000, subC, Gc);
         }
         tA = ex.group_sum_rt(tA, Gc);
         tB = ex.group_sum_rt(tB, Gc);
@@ -536,22 +557,27 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           const int cni = cn[i] << 4;
           int j = ln + 6 + subA;
           int offp = t4(i, j), offm = t4(ln + 1, j - 1);
+          int stepp = Ga * (j - 4) + gstep;          // column j -> j+Ga (and j-1 -> j-1+Ga is Ga less)
+          const int step2 = Ga * Ga;
+          const uint8_t* pc = cp + j;
           for (; j <= n; j += Ga) {
-            a += qb[offp] * H.FM[cni | cp[j]] * qm[offm];
-            offp += Ga * (j - 4) + gstep;            // column j -> j+Ga
-            offm += Ga * (j - 5) + gstep;            // column j-1 -> j-1+Ga
+            a += qb[offp] * H.RM[cni | pc[0]] * qm[offm];
+            offp += stepp;
+            offm += stepp - Ga;
+            stepp += step2;
+            pc += Ga;
           }
         }
         a = ex.group_sum_rt(a, Ga) * H.MLclosing;
         if (valid && subA == 0) {
-          const double c1 = qb[t4(i, ln + 1)] * H.MLclosing * H.FM[(cn[i] << 4) | cpl1];
+          const double c1 = qb[t4(i, ln + 1)] * H.MLclosing * H.RM[(cn[i] << 4) | cpl1];
           vB[i] = (cul1 ? vB[i] * eb1 : 0.) + c1;
           vA[i] = a;
         }
       }
     }
     // (c) level sums of the generic interior loops that enclose (k,ln)
-    const double* xI_rd = w.vecp(6 + (ln % 3));        // column ln+3
+    const double* col3 = qb + (((ln - 1) * (ln - 2)) >> 1);           // Pout*FI(i, ln+3) = col3[i - 1]
     for (int task = tid; task < 2 * R; task += nt) {
       if constexpr (E::kSerial)
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
@@ -566,12 +592,11 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         if (k >= 4 && ln + 3 <= n && smax >= 4) {
           const int upl_k1 = kCst ? (int)c.upl[k - 1] : 1000;
           const bool g = upl_k1 >= 1 && upr_l1 >= 1;
-          const int cnA = cn[k - 3] << 4;
           const bool ok1 = upl_k1 >= 2, ok2 = upr_l1 >= 2;
           const int k4 = k - 4;                      // row offset of (k-3, .)
-          const double* xi = xI_rd + k + 1;
+          const double* xi = col3 + k;               // xi[-S] = Pout*FI(k+1-S, ln+3)
           const int room1 = n + 1 - ln;              // border 1 needs j = ln+S-1 <= n
-#define ADP_B1 ((ok1 && upr_l1 >= S - 2 && S <= room1) ? qb[(((ln + S - 5) * (ln + S - 6)) >> 1) + k4] * H.FI[cnA | cp[ln + S - 1]] : 0.)
+#define ADP_B1 ((ok1 && upr_l1 >= S - 2 && S <= room1) ? qb[(((ln + S - 5) * (ln + S - 6)) >> 1) + k4] : 0.)
 #define ADP_B2 ((ok2 && upl_k1 >= S - 2 && S <= k) ? xi[-S] : 0.)
           if (par) { ADP_LEVEL_PASS(1, ADP_B1, ADP_B2) } else { ADP_LEVEL_PASS(0, ADP_B1, ADP_B2) }
 #undef ADP_B1
@@ -585,7 +610,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         for (int q = 0; q < kFastLevels; q++) w.dstate[(size_t)task * kFastLevels + q] = d[q];
     }
     // (d) the cells of this column that carry weight; the column's probability vector starts at zero
-    double* pcol = w.vecp((ln & 1) ? 16 : 2);
+    double* pcol = w.vecp((ln & 1) ? 6 : 2);
     int* counter = w.counter + (ln & 1);
     for (int r = tid; r < nr; r += nt) {
       pcol[r + 1] = 0.;
@@ -598,7 +623,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
 
   for (int l = n; l >= kTurn + 2; l--) {
     const int nr = l - 4;                       // rows k = 1 .. nr
-    double* pcol = w.vecp((l & 1) ? 16 : 2);
+    double* pcol = w.vecp((l & 1) ? 6 : 2);
     const int m = w.counter[l & 1];
     // ---- interval 1: outside weight of every listed pair (k,l)
     {
@@ -639,19 +664,19 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
               corner_u(q, &u1, &u2);
               if (u1 <= u1cap && u2 <= u2cap) {
                 const int i = k - 1 - u1, j = l + 1 + u2;
-                const double v = qb[t4(i, j)];
+                const double v = qb[t4(i, j)] * H.RI[(cn[i] << 4) | cp[j]];
                 if (v != 0.)
                   other += v * w.scaleG[u1 + u2 + 2] * interior_x(*G, G, u1, u2, pair_type(c.S[i], c.S[j]), t2r, c.S[i + 1], c.S[j - 1], sp1, sq1);
               }
             }
             // enclosing bulges with the run on the 3' side: i = k-1, j = l+1+u2, u2 >= 2
             {
-              const int si = sp1;
+              const int cni = cn[k - 1] << 4;
               int u2 = 2 + sub;
               int off = t4(k - 1, l + 1 + u2);
               for (; u2 <= u2cap; u2 += Gs) {
                 const int j = l + 1 + u2;
-                accB += qb[off] * au_factor(H, si, c.S[j]) * H.tapB[u2];
+                accB += qb[off] * H.RB[cni | cp[j]] * H.tapB[u2];
                 off += Gs * (j - 4) + gstep;
               }
             }
@@ -663,7 +688,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
               int off = t4(k - 2, l + 1 + u2);
               for (; u2 <= hi; u2 += Gs) {
                 const int j = l + 1 + u2;
-                acc1n += qb[off] * H.F1n[cni | cp[j]] * H.tap1n[u2];
+                acc1n += qb[off] * H.R1[cni | cp[j]] * H.tap1n[u2];
                 off += Gs * (j - 4) + gstep;
               }
             }
@@ -696,11 +721,11 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         val = ex.group_sum_rt(val, Gs);
         if (valid && sub == 0) {
           const int idx = t4(k, l);
-          const double qbv = qb[idx];
+          const double qbv = (k > 1 && l < n) ? qb[idx] * H.RI[cnl | cp[k]] : qb[idx];     // back to the plain Qb(k,l)
           pcol[k] = val * qbv;
           accq[k] += qbv * fast_stem_ext(c, G, type, k, l) * qln[l + 1];
           if (has_motif && is_motif_site(c, k, l)) pm[k] = val * fast_hairpin<kCst>(c, G, w, motif_boltz, k, l, type);
-          qb[idx] = val;
+          qb[idx] = val * H.FI[(cn[k] << 4) | cp[l]];       // outside weight, premultiplied (outer orientation)
         }
       }
     }
@@ -708,16 +733,14 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     // ---- interval 2: premultiplied vectors of the finished column; results; preparation of column l-1
     {
       double* x1n_wr = w.vecp(4 + (l & 1));
-      double* xI_wr = w.vecp(6 + (l % 3));
-      const int cpl = cp[l], sl = c.S[l];
+      const int cpl = cp[l];
       for (int r = tid; r < nr + 3; r += nt) {
         const int k = r + 1;
         double v = 0.;
         int code = 0;
-        if (k <= nr) { v = qb[t4(k, l)]; code = (cn[k] << 4) | cpl; }     // outer orientation
-        xA[k] = v * au_factor(H, c.S[k], sl);
-        x1n_wr[k] = v * H.F1n[code];
-        xI_wr[k] = v * H.FI[code];
+        if (k <= nr) { v = qb[t4(k, l)]; code = (cn[k] << 4) | cpl; }     // Pout * FI, outer orientation
+        xA[k] = v * H.RB[code];
+        x1n_wr[k] = v * H.R1[code];
       }
       if (out.bppm)
         for (int r = tid; r < nr; r += nt)

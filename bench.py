@@ -210,6 +210,7 @@ def main():
     from addapt_b200.capi import Problem
 
     torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = os.environ.get("ADDAPT_NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout: one JSON line only
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = addapt_b200.Engine(local)          # raises without the CUDA library / device: no fallback
