@@ -185,28 +185,29 @@ ADP_HD bool fast_codes(const E& ex, const SeqCtx& c, FastWork& w) {
 }
 
 // One level of the recursion for the thread that owns an anti-diagonal.  d[Q] holds the sum of level S = 4 + PAR + 2Q.
-// B1 / B2 evaluate to the two candidates with u1 = 2 / u2 = 2 (0. when the hard constraint forbids them); they
-// differ between the inside and the outside pass.  Everything indexed by S or Q is a compile-time constant, so d[]
-// stays in registers and the size factors are constant-bank operands.
-#define ADP_LEVEL_STEP(PAR, Q, B1, B2)                                                \
+// P1 / P2 are the ADDRESSES of the two candidates with u1 = 2 / u2 = 2 and C1 / C2 their hard-constraint gates; a level
+// that is off for this thread (S > smax, or the gate is closed) reads the always-zero word `zp` instead, so the step is
+// branch-free: every lane of the warp runs the same instructions whatever its row.  Everything indexed by S or Q is a
+// compile-time constant, so d[] stays in registers and the size factors are constant-bank operands.
+#define ADP_LEVEL_STEP(PAR, Q, P1, C1, P2, C2)                                         \
   if (4 + (PAR) + 2 * (Q) <= kMaxLoop) {                                              \
     constexpr int S = 4 + (PAR) + 2 * (Q);                                            \
-    double v = 0.;                                                                    \
-    if (S <= smax) {                                                                  \
-      double border = (B1);                                                           \
-      if (S > 4) border += (B2);                                                      \
-      v = ADP_FC.nin[S - 4 > 0 ? S - 4 : 0] * border;                                 \
-      if ((Q) > 0 && g) v += d[(Q) > 0 ? (Q) - 1 : 0];                                \
-      if (S >= 6) gen += ADP_FC.ip[S] * v;                                            \
-    }                                                                                 \
+    const bool on = S <= smax;                                                        \
+    const double* p1 = (on && (C1)) ? (P1) : zp;                                      \
+    const double* p2 = (S > 4 && on && (C2)) ? (P2) : zp;                             \
+    double v = ADP_FC.nin[S - 4 > 0 ? S - 4 : 0] * (*p1 + *p2);                       \
+    if ((Q) > 0) v += (on && g) ? d[(Q) > 0 ? (Q) - 1 : 0] : 0.;                      \
+    if (S >= 6) gen += ADP_FC.ip[S] * v;                                              \
     d[Q] = v;                                                                         \
   }
-#define ADP_LEVEL_PASS(PAR, B1, B2)                                                                                      \
-  ADP_LEVEL_STEP(PAR, 13, B1, B2) ADP_LEVEL_STEP(PAR, 12, B1, B2) ADP_LEVEL_STEP(PAR, 11, B1, B2)                       \
-  ADP_LEVEL_STEP(PAR, 10, B1, B2) ADP_LEVEL_STEP(PAR, 9, B1, B2) ADP_LEVEL_STEP(PAR, 8, B1, B2)                         \
-  ADP_LEVEL_STEP(PAR, 7, B1, B2) ADP_LEVEL_STEP(PAR, 6, B1, B2) ADP_LEVEL_STEP(PAR, 5, B1, B2)                          \
-  ADP_LEVEL_STEP(PAR, 4, B1, B2) ADP_LEVEL_STEP(PAR, 3, B1, B2) ADP_LEVEL_STEP(PAR, 2, B1, B2)                          \
-  ADP_LEVEL_STEP(PAR, 1, B1, B2) ADP_LEVEL_STEP(PAR, 0, B1, B2)
+#define ADP_LEVEL_PASS(PAR, B1, C1, B2, C2)                                                            \
+  ADP_LEVEL_STEP(PAR, 13, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 12, B1, C1, B2, C2) \
+  ADP_LEVEL_STEP(PAR, 11, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 10, B1, C1, B2, C2) \
+  ADP_LEVEL_STEP(PAR, 9, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 8, B1, C1, B2, C2) \
+  ADP_LEVEL_STEP(PAR, 7, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 6, B1, C1, B2, C2) \
+  ADP_LEVEL_STEP(PAR, 5, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 4, B1, C1, B2, C2) \
+  ADP_LEVEL_STEP(PAR, 3, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 2, B1, C1, B2, C2) \
+  ADP_LEVEL_STEP(PAR, 1, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 0, B1, C1, B2, C2)
 #define ADP_LEVEL_ZERO()                                                                                  \
   d[0] = d[1] = d[2] = d[3] = d[4] = d[5] = d[6] = d[7] = d[8] = d[9] = d[10] = d[11] = d[12] = d[13] = 0.;
 
@@ -254,6 +255,7 @@ template <bool kCst, class E>
 ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const PfTables* G, double motif_boltz, FastWork& w) {
   const int n = c.n, nt = ex.nthreads(), tid = ex.tid(), ld = w.ld, R = w.R;
   const int nt_lg = ilog2_floor((unsigned)nt), warp_lg = ilog2_floor((unsigned)E::kWarp);
+  const int half = E::kSerial ? R : (nt >> 1);      // anti-diagonal slots per level parity (>= R)
   const int ntri = (int)t4_count(n);
   double* const qb = w.qb;
   double* const qm = w.qm;
@@ -269,6 +271,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
   double* const gen0 = w.vecp(11);
   double* const gen1 = w.vecp(12);
   double d[kFastLevels];     // level sums of this thread's anti-diagonal (registers)
+  const double* const zp = &H.pad;   // an always-zero word for levels that are off
   ADP_LEVEL_ZERO()
   if constexpr (E::kSerial)
     for (int k = 0; k < 2 * R * kFastLevels; k++) w.dstate[k] = 0.;
@@ -292,11 +295,12 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     const double* qm1_prev = w.vecp((jn - 1) & 1);
     double* qm1_cur = w.vecp(jn & 1);
     int* counter = w.counter + (jn & 1);
-    for (int task = tid; task < 2 * R; task += nt) {
+    for (int task = tid; task < 2 * half; task += nt) {
+      const int par = task >= half ? 1 : 0;          // warp-uniform: the two parities are separate code paths
+      int key = task - par * half;
+      if (key >= R) continue;
       if constexpr (E::kSerial)
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
-      const int par = task >= R ? 1 : 0;
-      int key = task - par * R;
       if (key < jn + 1) key += R;
       const int i = key - jn;
       if (i >= 1 && i <= nr) {
@@ -308,12 +312,16 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
           const bool g = upr_i1 >= 1 && cuj1;
           const bool ok1 = upr_i1 >= 2, ok2 = upl_j1 >= 2;
           const double* xi = col3 + i;                 // xi[S] = Qb*FI(i+S-1, jn-3)
-          const int i2 = i + 2;
-#define ADP_B1 ((ok1 && upl_j1 >= S - 2) ? qb[(((jn - 3 - S) * (jn - 4 - S)) >> 1) + i2] : 0.)
-#define ADP_B2 ((ok2 && upr_i1 >= S - 2) ? xi[S] : 0.)
-          if (par) { ADP_LEVEL_PASS(1, ADP_B1, ADP_B2) } else { ADP_LEVEL_PASS(0, ADP_B1, ADP_B2) }
-#undef ADP_B1
-#undef ADP_B2
+          const double* qrow = qb + i + 2;             // Qb*FI(i+3, l) = qrow[(l-4)(l-5)/2]
+#define ADP_P1 (qrow + (((jn - 3 - S) * (jn - 4 - S)) >> 1))
+#define ADP_C1 (!kCst || (ok1 && upl_j1 >= S - 2))
+#define ADP_P2 (xi + S)
+#define ADP_C2 (!kCst || (ok2 && upr_i1 >= S - 2))
+          if (par) { ADP_LEVEL_PASS(1, ADP_P1, ADP_C1, ADP_P2, ADP_C2) } else { ADP_LEVEL_PASS(0, ADP_P1, ADP_C1, ADP_P2, ADP_C2) }
+#undef ADP_P1
+#undef ADP_C1
+#undef ADP_P2
+#undef ADP_C2
         } else {
           ADP_LEVEL_ZERO()
         }
@@ -502,6 +510,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
                          FastWork& w, const FastOut& out) {
   const int n = c.n, nt = ex.nthreads(), tid = ex.tid(), ld = w.ld, R = w.R;
   const int nt_lg = ilog2_floor((unsigned)nt), warp_lg = ilog2_floor((unsigned)E::kWarp);
+  const int half = E::kSerial ? R : (nt >> 1);      // anti-diagonal slots per level parity (>= R)
   double* const qb = w.qb;
   const double* const qm = w.qm;
   const uint8_t* const cn = w.cn;
@@ -524,6 +533,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   }
   for (int q = tid; q < out.n_query; q += nt) out.qprobs[q] = 0.;
   double d[kFastLevels];
+  const double* const zp = &H.pad;
   ADP_LEVEL_ZERO()
   if constexpr (E::kSerial)
     for (int k = 0; k < 2 * R * kFastLevels; k++) w.dstate[k] = 0.;
@@ -578,11 +588,12 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     }
     // (c) level sums of the generic interior loops that enclose (k,ln)
     const double* col3 = qb + (((ln - 1) * (ln - 2)) >> 1);           // Pout*FI(i, ln+3) = col3[i - 1]
-    for (int task = tid; task < 2 * R; task += nt) {
+    for (int task = tid; task < 2 * half; task += nt) {
+      const int par = task >= half ? 1 : 0;
+      int key = task - par * half;
+      if (key >= R) continue;
       if constexpr (E::kSerial)
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
-      const int par = task >= R ? 1 : 0;
-      int key = task - par * R;
       if (key < ln + 1) key += R;
       const int k = key - ln;
       if (k >= 1 && k <= nr) {
@@ -593,14 +604,18 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           const int upl_k1 = kCst ? (int)c.upl[k - 1] : 1000;
           const bool g = upl_k1 >= 1 && upr_l1 >= 1;
           const bool ok1 = upl_k1 >= 2, ok2 = upr_l1 >= 2;
-          const int k4 = k - 4;                      // row offset of (k-3, .)
+          const double* qrow = qb + k - 4;           // Pout*FI(k-3, j) = qrow[(j-4)(j-5)/2]
           const double* xi = col3 + k;               // xi[-S] = Pout*FI(k+1-S, ln+3)
           const int room1 = n + 1 - ln;              // border 1 needs j = ln+S-1 <= n
-#define ADP_B1 ((ok1 && upr_l1 >= S - 2 && S <= room1) ? qb[(((ln + S - 5) * (ln + S - 6)) >> 1) + k4] : 0.)
-#define ADP_B2 ((ok2 && upl_k1 >= S - 2 && S <= k) ? xi[-S] : 0.)
-          if (par) { ADP_LEVEL_PASS(1, ADP_B1, ADP_B2) } else { ADP_LEVEL_PASS(0, ADP_B1, ADP_B2) }
-#undef ADP_B1
-#undef ADP_B2
+#define ADP_P1 (qrow + (((ln + S - 5) * (ln + S - 6)) >> 1))
+#define ADP_C1 (S <= room1 && (!kCst || (ok1 && upr_l1 >= S - 2)))
+#define ADP_P2 (xi - S)
+#define ADP_C2 (S <= k && (!kCst || (ok2 && upl_k1 >= S - 2)))
+          if (par) { ADP_LEVEL_PASS(1, ADP_P1, ADP_C1, ADP_P2, ADP_C2) } else { ADP_LEVEL_PASS(0, ADP_P1, ADP_C1, ADP_P2, ADP_C2) }
+#undef ADP_P1
+#undef ADP_C1
+#undef ADP_P2
+#undef ADP_C2
         } else {
           ADP_LEVEL_ZERO()
         }
