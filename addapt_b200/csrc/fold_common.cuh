@@ -63,8 +63,21 @@ struct CtaExec {
   __device__ __forceinline__ int warp_bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
   // reduction over an aligned group of `g` lanes (g = power of two <= 32, uniform over the warp)
   __device__ __forceinline__ double group_sum_rt(double v, int g) const {
-    for (int o = g >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    // g is uniform over the warp: five straight-line butterfly steps, each skipped as a whole when the group is smaller
+    if (g > 16) v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (g > 8) v += __shfl_xor_sync(0xffffffffu, v, 8);
+    if (g > 4) v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (g > 2) v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (g > 1) v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
+  }
+  // two independent sums reduced together (the shuffles of one hide the latency of the other)
+  __device__ __forceinline__ void group_sum2_rt(double& a, double& b, int g) const {
+    if (g > 16) { a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16); }
+    if (g > 8) { a += __shfl_xor_sync(0xffffffffu, a, 8); b += __shfl_xor_sync(0xffffffffu, b, 8); }
+    if (g > 4) { a += __shfl_xor_sync(0xffffffffu, a, 4); b += __shfl_xor_sync(0xffffffffu, b, 4); }
+    if (g > 2) { a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2); }
+    if (g > 1) { a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1); }
   }
   __device__ __forceinline__ int atomic_inc(int* ctr) const { return atomicAdd(ctr, 1); }
   __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
@@ -89,6 +102,7 @@ struct SerialExec {
   int warp_first(bool flag) const { return flag ? 0 : -1; }
   int warp_bcast(int v, int) const { return v; }
   double group_sum_rt(double v, int) const { return v; }
+  void group_sum2_rt(double&, double&, int) const {}
   int atomic_inc(int* ctr) const { return (*ctr)++; }
   void warp_sync() const {}
 };

@@ -336,10 +336,9 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     }
   };
 
-  if (n >= 5) prepare_column(5);
   ex.sync();
-
-  for (int j = 5; j <= n; j++) {
+  // j = 4 is a warm-up turn without cells: it only prepares column 5 (one call site keeps the code small)
+  for (int j = 4; j <= n; j++) {
     const int nr = j - 4;                       // rows 1 .. nr
     const bool cuj = !kCst || can_unpair(c, j);
     const double* qm1_prev = w.vecp((j - 1) & 1);
@@ -466,8 +465,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
           tA = qm_row_terms(qm, qm1_cur, eMLbS, iA, nr, kCst ? (int)c.upr[iA] : 1000, subC, Gc);
           if (iB > iA) tB = qm_row_terms(qm, qm1_cur, eMLbS, iB, nr, kCst ? (int)c.upr[iB] : 1000, subC, Gc);
         }
-        tA = ex.group_sum_rt(tA, Gc);
-        tB = ex.group_sum_rt(tB, Gc);
+        ex.group_sum2_rt(tA, tB, Gc);
         if (valid && subC == 0) {
           qm[t4(iA, j)] = tA + qm1_cur[iA];
           if (iB > iA) qm[t4(iB, j)] = tB + qm1_cur[iB];
@@ -633,13 +631,11 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     }
   };
 
-  if (n >= kTurn + 2) prepare_column(n);
-  ex.sync();
-
-  for (int l = n; l >= kTurn + 2; l--) {
-    const int nr = l - 4;                       // rows k = 1 .. nr
+  // l = n+1 is a warm-up turn without cells: it only prepares column n (one call site keeps the code small)
+  for (int l = n + 1; l >= kTurn + 2; l--) {
+    const int nr = l <= n ? l - 4 : 0;          // rows k = 1 .. nr
     double* pcol = w.vecp((l & 1) ? 6 : 2);
-    const int m = w.counter[l & 1];
+    const int m = l <= n ? w.counter[l & 1] : 0;
     // ---- interval 1: outside weight of every listed pair (k,l)
     {
       if (tid == 0) w.counter[(l + 1) & 1] = 0;
