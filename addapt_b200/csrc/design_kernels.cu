@@ -9,6 +9,7 @@ extern __shared__ __align__(16) unsigned char adp_dsmem[];
 struct DesignSmem {
   void* fold_small;
   double* mats;
+  double* dstate;      // fast folds of constructs longer than threads/2: level sums in global scratch (else NULL)
   DesignScratch d;
 };
 
@@ -24,6 +25,9 @@ __device__ __forceinline__ DesignSmem carve_design_smem(int n_max, double* gmats
   } else {
     s.mats = gmats + (size_t)blockIdx.x * gmat_stride;
   }
+  s.dstate = nullptr;
+  if (kFast && n_max > fast_max_len((int)blockDim.x))
+    s.dstate = gmats + (size_t)blockIdx.x * gmat_stride + (kSmemMats ? 0 : fast_matrix_doubles(n_max));
   return s;
 }
 
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(512) score_batch_kernel(const ScoreBatchArgs a
     for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.seqs[(size_t)b * n + p];
     __syncthreads();
     bool declined = false;
-    const double sc = score_construct<kFast>(ex, a.sp, s.d.cur, s.d, s.fold_small, s.mats, &declined);
+    const double sc = score_construct<kFast>(ex, a.sp, s.d.cur, s.d, s.fold_small, s.mats, &declined, s.dstate);
     if (declined) {
       if (threadIdx.x == 0) { a.redo[b] = 1; atomicAdd(a.redo + a.B, 1); }
     } else {
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
   for (int t = blockIdx.x; t < a.n_traj; t += gridDim.x) {
     for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.init_seq[p];
     __syncthreads();
-    mc_trajectory<kFast>(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.n_steps, a.thermo_kind, a.thermo_args, s.d, s.fold_small, s.mats, &res);
+    mc_trajectory<kFast>(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.n_steps, a.thermo_kind, a.thermo_args, s.d, s.fold_small, s.mats, &res, s.dstate);
     __syncthreads();
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
       if (a.final_seq) a.final_seq[(size_t)t * n + p] = s.d.cur[p];
@@ -87,7 +91,7 @@ LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs, bool fast) {
   const size_t mats = nmat * sizeof(double);
   p.mats_in_smem = small + mats <= d.smem_optin;
   p.smem_bytes = p.mats_in_smem ? small + mats : small;
-  p.gmat_stride = p.mats_in_smem ? 0 : nmat;
+  p.gmat_stride = (p.mats_in_smem ? 0 : nmat) + ((fast && n_max > fast_max_len(p.threads)) ? fast_state_doubles(n_max) : 0);
   size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);
   size_t by_threads = 2048 / p.threads;
   if (fast && by_threads > 2) by_threads = 2;               // 128 registers per thread

@@ -307,7 +307,7 @@ static int run_pf(adp_engine* e, int B, int n, const uint8_t* d_seqs, int V, con
     ADP_CUDA(e, e->b_redo.ensure((size_t)(jobs + 1) * sizeof(int)));
     ADP_CUDA(e, cudaMemsetAsync(e->b_redo.p, 0, (size_t)(jobs + 1) * sizeof(int), e->stream));
     a.redo = (int*)e->b_redo.p;
-    if (!pfast.mats_in_smem) {
+    if (pfast.gmat_stride) {
       ADP_CUDA(e, e->b_gmats.ensure((size_t)pfast.grid * pfast.gmat_stride * sizeof(double)));
       a.gmats = (double*)e->b_gmats.p;
       a.gmat_stride = pfast.gmat_stride;

@@ -71,6 +71,14 @@ struct CtaExec {
     if (g > 1) v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
   }
+  __device__ __forceinline__ int group_min_rt(int v, int g) const {
+    if (g > 16) v = min(v, __shfl_xor_sync(0xffffffffu, v, 16));
+    if (g > 8) v = min(v, __shfl_xor_sync(0xffffffffu, v, 8));
+    if (g > 4) v = min(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    if (g > 2) v = min(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    if (g > 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return v;
+  }
   // two independent sums reduced together (the shuffles of one hide the latency of the other)
   __device__ __forceinline__ void group_sum2_rt(double& a, double& b, int g) const {
     if (g > 16) { a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16); }
@@ -103,6 +111,7 @@ struct SerialExec {
   int warp_bcast(int v, int) const { return v; }
   double group_sum_rt(double v, int) const { return v; }
   void group_sum2_rt(double&, double&, int) const {}
+  int group_min_rt(int v, int) const { return v; }
   int atomic_inc(int* ctr) const { return (*ctr)++; }
   void warp_sync() const {}
 };

@@ -174,7 +174,7 @@ ADP_HD void run_mfe_job(const E& ex, const MfeJob& job, void* small, int32_t* ma
   const int e = mfe_fill(ex, c, *job.T, mdcal, w);
   if (ex.tid() == 0) *job.e_dcal = e;
   if (!job.structure) return;
-  if (ex.warp() == 0) mfe_traceback(ex, c, *job.T, job.motif, mdcal, w);
+  if (ex.warp() == 0) mfe_traceback(ex, c, *job.T, job.motif, mdcal, TriView{w.C, w.F}, w);
   ex.sync();
   for (int p = ex.tid(); p < n; p += ex.nthreads()) job.structure[p] = w.out[p];
 }

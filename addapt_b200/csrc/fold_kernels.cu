@@ -107,9 +107,14 @@ __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) pf_fast_ker
   } else {
     mats = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
   }
+  // constructs longer than threads/2 have more anti-diagonals than threads: their level sums live in the CTA's slab of
+  // global scratch (behind the matrices when those are global too)
+  double* dstate = nullptr;
+  if (n > fast_max_len(kThreads))
+    dstate = a.gmats + (size_t)blockIdx.x * a.gmat_stride + (kSmemMats ? 0 : fast_matrix_doubles(n));
   for (int jid = blockIdx.x; jid < jobs; jid += gridDim.x) {
     const PfJob job = make_pf_job(a, jid);
-    const bool done = run_pf_job_fast(ex, job, small, mats);
+    const bool done = run_pf_job_fast(ex, job, small, mats, dstate);
     if (!done && threadIdx.x == 0) { a.redo[jid] = 1; atomicAdd(a.redo + jobs, 1); }
     __syncthreads();   // the next job reuses the working set
   }
@@ -198,14 +203,16 @@ cudaError_t launch_pf(const PfBatchArgs& a, const LaunchPlan& p, cudaStream_t st
 
 LaunchPlan plan_pf_fast(const DeviceInfo& d, int n, int jobs) {
   LaunchPlan p{};
-  p.threads = n <= fast_max_len(256) ? 256 : n <= fast_max_len(512) ? 512 : 0;
+  // 256 threads keep the level sums of n <= 128 in registers with two CTAs per SM; 512 threads serve n <= 256 the same way and
+  // longer constructs (up to kFastMaxN) with the sums in global scratch
+  p.threads = n <= fast_max_len(256) ? 256 : n <= kFastMaxN ? 512 : 0;
   if (!p.threads) return p;
   p.group = 1;
   const size_t small_al = (fast_small_bytes(n) + 15) & ~(size_t)15;
   const size_t mats_bytes = fast_matrix_doubles(n) * sizeof(double);
   p.mats_in_smem = small_al + mats_bytes <= d.smem_optin;
   p.smem_bytes = p.mats_in_smem ? small_al + mats_bytes : small_al;
-  p.gmat_stride = p.mats_in_smem ? 0 : fast_matrix_doubles(n);
+  p.gmat_stride = (p.mats_in_smem ? 0 : fast_matrix_doubles(n)) + (n > fast_max_len(p.threads) ? fast_state_doubles(n) : 0);
   size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);   // 1 KB reserved per resident CTA
   size_t by_threads = p.threads == 256 ? 2 : 1;            // __launch_bounds__ of pf_fast_kernel
   size_t occ = per_sm < by_threads ? per_sm : by_threads;

@@ -142,10 +142,19 @@ ADP_HD int mfe_fill(const E& ex, const SeqCtx& c, const IntTables& P, int motif_
   return w.f5[n];
 }
 
+// How the traceback reads the filled matrices: c(i,j) = C(i,j), f(i,j) = F(i,j), kInf where no structure exists.
+struct TriView {
+  const int32_t* C;
+  const int32_t* F;
+  ADP_HD int c(int i, int j) const { return C[tri(i, j)]; }
+  ADP_HD int f(int i, int j) const { return F[tri(i, j)]; }
+};
+
 // Traceback by warp 0 of the CTA (all its lanes must call).  Section kinds: 0 = exterior prefix f5(j),
-// 1 = multiloop part F(i,j), 2 = pair (i,j).
-template <class E>
-ADP_HD void mfe_traceback(const E& ex, const SeqCtx& c, const IntTables& P, const MotifDev* motif, int motif_dcal, MfeWork& w) {
+// 1 = multiloop part F(i,j), 2 = pair (i,j).  `view` abstracts the matrix layout (general kernel: full triangles;
+// fast kernel: trimmed, premultiplied triangles); w supplies f5, the section stack and the output string.
+template <class E, class View>
+ADP_HD void mfe_traceback(const E& ex, const SeqCtx& c, const IntTables& P, const MotifDev* motif, int motif_dcal, const View& view, MfeWork& w) {
   const int n = c.n, lane = ex.lane();
   constexpr int W = E::kWarp;
   for (int p = lane; p < n; p += W) w.out[p] = '.';
@@ -179,7 +188,7 @@ ADP_HD void mfe_traceback(const E& ex, const SeqCtx& c, const IntTables& P, cons
         bool hit = false;
         if (k >= 1) {
           const int type = allowed_type(c, k, j);
-          const int cv = w.C[tri(k, j)];
+          const int cv = view.c(k, j);
           if (type && cv < kInf && w.f5[k - 1] < kInf) hit = w.f5[j] == w.f5[k - 1] + cv + stem_e_at(P, c, type, k, j, true);
         }
         const int first = ex.warp_first(hit);
@@ -191,7 +200,7 @@ ADP_HD void mfe_traceback(const E& ex, const SeqCtx& c, const IntTables& P, cons
     } else if (kind == 2) {
       if (lane == 0) { w.out[i - 1] = '('; w.out[j - 1] = ')'; }
       const int type = allowed_type(c, i, j);
-      const int e = w.C[tri(i, j)];
+      const int e = view.c(i, j);
       if (e == hairpin_cell_e(P, c, motif_dcal, i, j, type)) {
         if (motif && is_motif_site(c, i, j) && lane == 0)
           for (int q = 0; q < motif->n_pairs; q++) { w.out[i - 1 + motif->pair_i[q]] = '('; w.out[i - 1 + motif->pair_j[q]] = ')'; }
@@ -214,7 +223,7 @@ ADP_HD void mfe_traceback(const E& ex, const SeqCtx& c, const IntTables& P, cons
           bool hit = false;
           if (u2 <= u2max) {
             const int l = j - 1 - u2;
-            const int v = w.C[tri(k, l)];
+            const int v = view.c(k, l);
             if (v < kInf) {
               const int t2 = pair_type(c.S[k], c.S[l]);
               hit = e == v + interior_e(P, u1, u2, type, rtype(t2), si1, sj1, c.S[k - 1], c.S[l + 1]);
@@ -232,7 +241,7 @@ ADP_HD void mfe_traceback(const E& ex, const SeqCtx& c, const IntTables& P, cons
         const int k = base + lane;
         bool hit = false;
         if (k <= j - 1) {
-          const int a = w.F[tri(i + 1, k - 1)], b = w.F[tri(k, j - 1)];
+          const int a = view.f(i + 1, k - 1), b = view.f(k, j - 1);
           hit = a < kInf && b < kInf && e == a + b + cl;
         }
         const int first = ex.warp_first(hit);
@@ -242,17 +251,17 @@ ADP_HD void mfe_traceback(const E& ex, const SeqCtx& c, const IntTables& P, cons
       ADP_PUSH(i + 1, found - 1, 1);
       ADP_PUSH(found, j - 1, 1);
     } else {
-      const int e = w.F[tri(i, j)];
-      if (j - 1 >= i && can_unpair(c, j) && w.F[tri(i, j - 1)] < kInf && e == w.F[tri(i, j - 1)] + mlb) { ADP_PUSH(i, j - 1, 1); continue; }
-      if (i + 1 <= j && can_unpair(c, i) && w.F[tri(i + 1, j)] < kInf && e == w.F[tri(i + 1, j)] + mlb) { ADP_PUSH(i + 1, j, 1); continue; }
+      const int e = view.f(i, j);
+      if (j - 1 >= i && can_unpair(c, j) && view.f(i, j - 1) < kInf && e == view.f(i, j - 1) + mlb) { ADP_PUSH(i, j - 1, 1); continue; }
+      if (i + 1 <= j && can_unpair(c, i) && view.f(i + 1, j) < kInf && e == view.f(i + 1, j) + mlb) { ADP_PUSH(i + 1, j, 1); continue; }
       const int type = allowed_type(c, i, j);
-      if (type && w.C[tri(i, j)] < kInf && e == w.C[tri(i, j)] + stem_e_at(P, c, type, i, j, false)) { ADP_PUSH(i, j, 2); continue; }
+      if (type && view.c(i, j) < kInf && e == view.c(i, j) + stem_e_at(P, c, type, i, j, false)) { ADP_PUSH(i, j, 2); continue; }
       int found = -1;
       for (int base = i + 1; base <= j && found < 0; base += W) {
         const int k = base + lane;
         bool hit = false;
         if (k <= j) {
-          const int a = w.F[tri(i, k - 1)], b = w.F[tri(k, j)];
+          const int a = view.f(i, k - 1), b = view.f(k, j);
           hit = a < kInf && b < kInf && e == a + b;
         }
         const int first = ex.warp_first(hit);

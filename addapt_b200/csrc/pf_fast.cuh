@@ -30,6 +30,7 @@
 namespace adp {
 
 constexpr int kFastLevels = 14;       // level sums per thread: s = 4+par, 6+par, ..., 30+par
+constexpr int kFastMaxN = 320;        // longest construct the fast path takes (ADP_MAX_LEN)
 
 struct PfHot {                        // shared memory, staged once per CTA
   double FI[256], F1n[256], FM[256];  // mismatch_interior, mismatch_interior_1n, multiloop stem factor (closing orientation)
@@ -104,7 +105,8 @@ struct FastWork {
   uint8_t* cp;     // [ld] code of (S[p], S[p-1])
   uint16_t* cells; // [ld] rows of the current column that can pair
   int* counter;    // [4]: 0/1 list lengths by column parity, 2 "declined" flag
-  double* dstate;  // host emulation only: the level sums every "thread" keeps in registers  [2*R*kFastLevels]
+  double* dstate;  // NULL: every thread keeps the level sums of its anti-diagonal in registers (needs 2*R <= threads);
+                   // else [2*R*kFastLevels] doubles of memory holding them (host emulation; constructs longer than threads/2)
   int ld;          // vector length (>= n + 4)
   int R;           // anti-diagonal slots (fast_R); the CTA needs 2*R threads
 };
@@ -114,7 +116,8 @@ ADP_HD int t4(int i, int j) { return (((j - 4) * (j - 5)) >> 1) + (i - 1); }
 ADP_HD size_t t4_count(int n) { return n >= 5 ? (size_t)(n - 4) * (n - 3) / 2 : 0; }
 ADP_HD int fast_ld(int n) { return (n + 6) & ~1; }
 ADP_HD int fast_R(int n) { return n < 4 ? 4 : n; }      // anti-diagonal keys i+j <= 2n-4 < 2R, live window < R
-ADP_HD int fast_max_len(int threads) { return threads / 2; }
+ADP_HD int fast_max_len(int threads) { return threads / 2; }      // longest construct with register-resident level sums
+ADP_HD size_t fast_state_doubles(int n) { return (size_t)2 * fast_R(n) * kFastLevels; }
 
 ADP_HD size_t fast_small_bytes(int n) {
   const size_t ld = (size_t)fast_ld(n);
@@ -255,7 +258,8 @@ template <bool kCst, class E>
 ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const PfTables* G, double motif_boltz, FastWork& w) {
   const int n = c.n, nt = ex.nthreads(), tid = ex.tid(), ld = w.ld, R = w.R;
   const int nt_lg = ilog2_floor((unsigned)nt), warp_lg = ilog2_floor((unsigned)E::kWarp);
-  const int half = E::kSerial ? R : (nt >> 1);      // anti-diagonal slots per level parity (>= R)
+  const bool mem_state = E::kSerial || w.dstate != nullptr;   // level sums in memory: host emulation, or more anti-diagonals than threads
+  const int half = mem_state ? R : (nt >> 1);        // anti-diagonal slots per level parity (>= R)
   const int ntri = (int)t4_count(n);
   double* const qb = w.qb;
   double* const qm = w.qm;
@@ -273,8 +277,8 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
   double d[kFastLevels];     // level sums of this thread's anti-diagonal (registers)
   const double* const zp = &H.pad;   // an always-zero word for levels that are off
   ADP_LEVEL_ZERO()
-  if constexpr (E::kSerial)
-    for (int k = 0; k < 2 * R * kFastLevels; k++) w.dstate[k] = 0.;
+  if (mem_state)
+    for (int k = tid; k < 2 * R * kFastLevels; k += nt) w.dstate[k] = 0.;
   if (tid == 0) { w.counter[0] = 0; w.counter[1] = 0; }
   ex.sync();
   const double s1 = H.scale1, eb1 = H.eMLb1;
@@ -299,7 +303,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       const int par = task >= half ? 1 : 0;          // warp-uniform: the two parities are separate code paths
       int key = task - par * half;
       if (key >= R) continue;
-      if constexpr (E::kSerial)
+      if (mem_state)
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
       if (key < jn + 1) key += R;
       const int i = key - jn;
@@ -327,7 +331,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         }
         (par ? gen1 : gen0)[i] = gen;
       }
-      if constexpr (E::kSerial)
+      if (mem_state)
         for (int q = 0; q < kFastLevels; q++) w.dstate[(size_t)task * kFastLevels + q] = d[q];
     }
     for (int r = tid; r < nr; r += nt) {
@@ -508,7 +512,8 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
                          FastWork& w, const FastOut& out) {
   const int n = c.n, nt = ex.nthreads(), tid = ex.tid(), ld = w.ld, R = w.R;
   const int nt_lg = ilog2_floor((unsigned)nt), warp_lg = ilog2_floor((unsigned)E::kWarp);
-  const int half = E::kSerial ? R : (nt >> 1);      // anti-diagonal slots per level parity (>= R)
+  const bool mem_state = E::kSerial || w.dstate != nullptr;   // level sums in memory: host emulation, or more anti-diagonals than threads
+  const int half = mem_state ? R : (nt >> 1);        // anti-diagonal slots per level parity (>= R)
   double* const qb = w.qb;
   const double* const qm = w.qm;
   const uint8_t* const cn = w.cn;
@@ -533,8 +538,8 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   double d[kFastLevels];
   const double* const zp = &H.pad;
   ADP_LEVEL_ZERO()
-  if constexpr (E::kSerial)
-    for (int k = 0; k < 2 * R * kFastLevels; k++) w.dstate[k] = 0.;
+  if (mem_state)
+    for (int k = tid; k < 2 * R * kFastLevels; k += nt) w.dstate[k] = 0.;
   if (tid == 0) { w.counter[0] = 0; w.counter[1] = 0; }
   ex.sync();
   if (tid == 0) { qln[n + 1] = 1.; qln[n + 2] = 0.; }
@@ -590,7 +595,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       const int par = task >= half ? 1 : 0;
       int key = task - par * half;
       if (key >= R) continue;
-      if constexpr (E::kSerial)
+      if (mem_state)
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
       if (key < ln + 1) key += R;
       const int k = key - ln;
@@ -619,7 +624,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         }
         (par ? gen1 : gen0)[k] = gen;
       }
-      if constexpr (E::kSerial)
+      if (mem_state)
         for (int q = 0; q < kFastLevels; q++) w.dstate[(size_t)task * kFastLevels + q] = d[q];
     }
     // (d) the cells of this column that carry weight; the column's probability vector starts at zero
