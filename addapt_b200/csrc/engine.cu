@@ -280,10 +280,25 @@ int adp_mfe_batch(adp_engine* e, int B, int n, const uint8_t* seqs, const char* 
   if ((rc = stage_in(e, e->b_seqs, seqs, (size_t)B * n, &a.seqs))) return rc;
   if ((rc = stage_out(e, e->b_e, e_dcal, (size_t)B, &a.e_dcal))) return rc;
   if ((rc = stage_out(e, e->b_structs, structs, (size_t)B * n, &a.structs))) return rc;
+  LaunchPlan pfast = plan_mfe_fast(e->info, n, B);
+  if (pfast.threads && !e->force_general) {
+    // fast kernel first; it flags the sequences it declines (letters outside ACGU/T), which the general kernel then folds
+    ADP_CUDA(e, e->b_redo.ensure((size_t)(B + 1) * sizeof(int)));
+    ADP_CUDA(e, cudaMemsetAsync(e->b_redo.p, 0, (size_t)(B + 1) * sizeof(int), e->stream));
+    a.redo = (int*)e->b_redo.p;
+    if (pfast.gmat_stride) {
+      ADP_CUDA(e, e->b_gmats.ensure((size_t)pfast.grid * pfast.gmat_stride * sizeof(int32_t)));
+      a.gmats = (int32_t*)e->b_gmats.p;
+      a.gmat_stride = pfast.gmat_stride;
+    }
+    ADP_CUDA(e, launch_mfe_fast(a, pfast, &e->model.mfe(), e->stream));
+    e->launches++;
+    a.only_redo = 1;
+  }
   LaunchPlan p = plan_mfe(e->info, n, B);
   if (!p.mats_in_smem) {
-    ADP_CUDA(e, e->b_gmats.ensure((size_t)p.grid * p.gmat_stride * sizeof(int32_t)));
-    a.gmats = (int32_t*)e->b_gmats.p;
+    ADP_CUDA(e, e->b_gmats2.ensure((size_t)p.grid * p.gmat_stride * sizeof(int32_t)));
+    a.gmats = (int32_t*)e->b_gmats2.p;
     a.gmat_stride = p.gmat_stride;
   }
   ADP_CUDA(e, launch_mfe(a, p, e->stream));

@@ -5,6 +5,7 @@
 #include "mfe_core.cuh"
 #include "pf_core.cuh"
 #include "pf_fast.cuh"
+#include "mfe_fast.cuh"
 
 namespace adp {
 
@@ -177,6 +178,57 @@ ADP_HD void run_mfe_job(const E& ex, const MfeJob& job, void* small, int32_t* ma
   if (ex.warp() == 0) mfe_traceback(ex, c, *job.T, job.motif, mdcal, TriView{w.C, w.F}, w);
   ex.sync();
   for (int p = ex.tid(); p < n; p += ex.nthreads()) job.structure[p] = w.out[p];
+}
+
+// The fast path (mfe_fast.cuh) for the same job.  `small`: mfe_fast_small_bytes(n); `mats`: mfe_fast_matrix_ints(n) int32
+// (shared or global); `dstate`: see run_pf_job_fast.  Returns false (nothing written) for letters outside ACGU/T.
+template <class E>
+ADP_HD bool run_mfe_job_fast(const E& ex, const MfeJob& job, void* small, int32_t* mats, int32_t* dstate = nullptr) {
+  const int n = job.n;
+  Carver cv(small);
+  MfeHot* H = cv.take<MfeHot>(1);
+  SeqCtx c;
+  carve_ctx(cv, c, n);
+  MfeFastWork w;
+  w.ld = fast_ld(n);
+  w.R = fast_R(n);
+  w.vbase = cv.take<int32_t>((size_t)kMfeFastVectors * w.ld);
+  w.cn = cv.take<uint8_t>(w.ld);
+  w.cp = cv.take<uint8_t>(w.ld);
+  w.cells = cv.take<uint16_t>(w.ld);
+  w.counter = cv.take<int>(4);
+  MfeWork tb;                              // what the shared traceback needs besides the matrices
+  tb.stack = cv.take<int16_t>((size_t)(4 * n + 16) * 3);
+  tb.out = cv.take<char>(n + 16);
+  tb.C = nullptr; tb.F = nullptr; tb.fm1a = nullptr; tb.fm1b = nullptr; tb.ext = nullptr;
+  w.C = mats;
+  w.F = mats + t4_count(n) + 2;
+  w.dstate = dstate;
+  c.has_cst = job.cst != nullptr;
+  c.motif_len = job.motif ? job.motif->len : 0;
+  const int mdcal = job.motif ? job.motif->contrib_dcal : 0;
+  if (ex.tid() == 0) w.counter[2] = 0;
+  stage_mfe_hot(ex, H, job.T);
+  load_context(ex, c, job.seq, job.cst, job.motif);   // ends with a barrier
+  {
+    // position codes, shared with the PF fast path
+    FastWork codes;
+    codes.ld = w.ld;
+    codes.cn = w.cn;
+    codes.cp = w.cp;
+    if (!fast_codes(ex, c, codes)) w.counter[2] = 1;
+  }
+  ex.sync();
+  if (w.counter[2]) return false;
+
+  const int e = c.has_cst ? mfe_fast_fill<true>(ex, c, *H, *job.T, mdcal, w) : mfe_fast_fill<false>(ex, c, *H, *job.T, mdcal, w);
+  if (ex.tid() == 0) *job.e_dcal = e;
+  if (!job.structure) return true;
+  tb.f5 = w.vecp(6);
+  if (ex.warp() == 0) mfe_traceback(ex, c, *job.T, job.motif, mdcal, FastMfeView{w.C, w.F, H->FI, w.cn, w.cp, n}, tb);
+  ex.sync();
+  for (int p = ex.tid(); p < n; p += ex.nthreads()) job.structure[p] = tb.out[p];
+  return true;
 }
 
 }  // namespace adp

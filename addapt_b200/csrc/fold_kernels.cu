@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(512) mfe_batch_kernel(const MfeBatchArgs a) {
   } else {
     mats = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
   }
+  if (a.only_redo && a.redo[a.B] == 0) return;
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    if (a.only_redo && !a.redo[b]) continue;
     MfeJob job;
     job.seq = a.seqs + (size_t)b * n;
     job.n = n;
@@ -117,6 +119,37 @@ __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) pf_fast_ker
     const bool done = run_pf_job_fast(ex, job, small, mats, dstate);
     if (!done && threadIdx.x == 0) { a.redo[jid] = 1; atomicAdd(a.redo + jobs, 1); }
     __syncthreads();   // the next job reuses the working set
+  }
+}
+
+// Fast MFE path (mfe_fast.cuh): int32 matrices are half the size of the PF ones, so up to four constructs share an SM.
+template <int kThreads, bool kSmemMats>
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 3 : 1) mfe_fast_kernel(const MfeBatchArgs a) {
+  CtaExec<1> ex;
+  const int n = a.n;
+  void* small = adp_smem;
+  int32_t* mats;
+  if (kSmemMats) {
+    size_t off = (mfe_fast_small_bytes(n) + 15) & ~(size_t)15;
+    mats = reinterpret_cast<int32_t*>(adp_smem + off);
+  } else {
+    mats = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
+  }
+  int32_t* dstate = nullptr;
+  if (n > fast_max_len(kThreads))
+    dstate = a.gmats + (size_t)blockIdx.x * a.gmat_stride + (kSmemMats ? 0 : mfe_fast_matrix_ints(n));
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    MfeJob job;
+    job.seq = a.seqs + (size_t)b * n;
+    job.n = n;
+    job.cst = a.cst;
+    job.motif = a.motif;
+    job.T = a.T;
+    job.e_dcal = a.e_dcal + b;
+    job.structure = a.structs ? a.structs + (size_t)b * n : nullptr;
+    const bool done = run_mfe_job_fast(ex, job, small, mats, dstate);
+    if (!done && threadIdx.x == 0) { a.redo[b] = 1; atomicAdd(a.redo + a.B, 1); }
+    __syncthreads();
   }
 }
 
@@ -235,6 +268,40 @@ cudaError_t launch_pf_fast(const PfBatchArgs& a, const LaunchPlan& p, const PfTa
   }
   if (p.mats_in_smem) ADP_LAUNCH((pf_fast_kernel<512, true>), a);
   ADP_LAUNCH((pf_fast_kernel<512, false>), a);
+}
+
+LaunchPlan plan_mfe_fast(const DeviceInfo& d, int n, int jobs) {
+  LaunchPlan p{};
+  p.threads = n <= fast_max_len(256) ? 256 : n <= kFastMaxN ? 512 : 0;
+  if (!p.threads) return p;
+  p.group = 1;
+  const size_t small_al = (mfe_fast_small_bytes(n) + 15) & ~(size_t)15;
+  const size_t mats_bytes = mfe_fast_matrix_ints(n) * sizeof(int32_t);
+  p.mats_in_smem = small_al + mats_bytes <= d.smem_optin;
+  p.smem_bytes = p.mats_in_smem ? small_al + mats_bytes : small_al;
+  p.gmat_stride = (p.mats_in_smem ? 0 : mfe_fast_matrix_ints(n)) + (n > fast_max_len(p.threads) ? fast_state_doubles(n) : 0);
+  size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);
+  size_t by_threads = p.threads == 256 ? 3 : 1;            // __launch_bounds__ of mfe_fast_kernel
+  size_t occ = per_sm < by_threads ? per_sm : by_threads;
+  if (occ < 1) occ = 1;
+  long grid = (long)d.sm_count * (long)occ;
+  if (grid > jobs) grid = jobs;
+  if (grid < 1) grid = 1;
+  p.grid = (int)grid;
+  return p;
+}
+
+cudaError_t launch_mfe_fast(const MfeBatchArgs& a, const LaunchPlan& p, const IntTables* host_tables, cudaStream_t stream) {
+  FastConstI fc;
+  fill_fast_const_i(&fc, host_tables);
+  cudaError_t ce = cudaMemcpyToSymbolAsync(c_fast_const_i, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
+  if (ce != cudaSuccess) return ce;
+  if (p.threads == 256) {
+    if (p.mats_in_smem) ADP_LAUNCH((mfe_fast_kernel<256, true>), a);
+    ADP_LAUNCH((mfe_fast_kernel<256, false>), a);
+  }
+  if (p.mats_in_smem) ADP_LAUNCH((mfe_fast_kernel<512, true>), a);
+  ADP_LAUNCH((mfe_fast_kernel<512, false>), a);
 }
 
 cudaError_t launch_mfe(const MfeBatchArgs& a, const LaunchPlan& p, cudaStream_t stream) {

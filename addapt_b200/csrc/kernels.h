@@ -39,6 +39,8 @@ struct MfeBatchArgs {
   char* structs;               // NULL or [B*n]
   int32_t* gmats;
   size_t gmat_stride;          // ints per CTA
+  int* redo;                   // [B + 1] or NULL: folds the fast kernel declined (non-ACGU letters); last = their count
+  int only_redo;               // general kernel: fold only the flagged sequences
 };
 
 struct LaunchPlan {
@@ -57,6 +59,8 @@ struct DeviceInfo {
 LaunchPlan plan_pf(const DeviceInfo&, int n, int jobs, bool any_outside);
 // fast path (pf_fast.cuh); plan.threads == 0 when the length is outside its range
 LaunchPlan plan_pf_fast(const DeviceInfo&, int n, int jobs);
+LaunchPlan plan_mfe_fast(const DeviceInfo&, int n, int jobs);
+cudaError_t launch_mfe_fast(const MfeBatchArgs&, const LaunchPlan&, const IntTables* host_tables, cudaStream_t);
 // host_tables: the engine's Boltzmann tables on the host (their size-indexed factors go to the constant bank)
 cudaError_t launch_pf_fast(const PfBatchArgs&, const LaunchPlan&, const PfTables* host_tables, cudaStream_t);
 LaunchPlan plan_mfe(const DeviceInfo&, int n, int jobs);

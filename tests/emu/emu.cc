@@ -90,6 +90,32 @@ int emu_pf(void* model, int n, const char* seq, const char* cst, const char* mse
   } catch (std::string& er) { g_err = er; return -1; }
 }
 
+// fast = 1: mfe_fast.cuh; returns 1 when it declines the sequence
+int emu_mfe2(void* model, int n, const char* seq, const char* cst, const char* mseq, const char* mfold, double kd_uM,
+             int32_t* e, char* structure, int fast) {
+  auto* M = (EnergyModel*)model;
+  try {
+    ConstraintDev cd;
+    MotifDev md;
+    if (cst) build_constraint(cst, n, &cd);
+    if (mseq) md = M->make_motif(mseq, mfold, M->kT_kcal() * std::log(kd_uM / 1e6));
+    MfeJob job{};
+    job.seq = (const uint8_t*)seq; job.n = n; job.cst = cst ? &cd : nullptr; job.motif = mseq ? &md : nullptr;
+    job.T = &M->mfe(); job.e_dcal = e; job.structure = structure;
+    SerialExec ex;
+    if (fast) {
+      std::vector<char> small(mfe_fast_small_bytes(n) + 64);
+      std::vector<int32_t> mats(mfe_fast_matrix_ints(n) + 2);
+      std::vector<int32_t> dstate((size_t)2 * fast_R(n) * kFastLevels + 2);
+      return run_mfe_job_fast(ex, job, small.data(), mats.data(), dstate.data()) ? 0 : 1;
+    }
+    std::vector<char> small(mfe_small_bytes(n) + 64);
+    std::vector<int32_t> mats(mfe_matrix_ints(n) + 2);
+    run_mfe_job(ex, job, small.data(), mats.data());
+    return 0;
+  } catch (std::string& er) { g_err = er; return -1; }
+}
+
 int emu_mfe(void* model, int n, const char* seq, const char* cst, const char* mseq, const char* mfold, double kd_uM,
             int32_t* e, char* structure) {
   auto* M = (EnergyModel*)model;

@@ -25,6 +25,8 @@ class Emu:
                               C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_mfe.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double,
                               C.POINTER(C.c_int32), C.c_char_p]
+        L.emu_mfe2.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double,
+                               C.POINTER(C.c_int32), C.c_char_p, C.c_int]
         L.emu_score.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_mc.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double),
                              C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int32),
@@ -70,12 +72,14 @@ class Emu:
             return dg.value, bp, qp[:nq]
         return (dg.value, bp) if bppm else dg.value
 
-    def mfe(self, seq, cst=None, motif=None):
+    def mfe(self, seq, cst=None, motif=None, fast=False):
         n = len(seq)
         e = C.c_int32()
         st = C.create_string_buffer(n + 1)
-        rc = self.lib.emu_mfe(self.model, n, _b(seq), _b(cst) if cst else None, _b(motif[0]) if motif else None,
-                              _b(motif[1]) if motif else None, motif[2] if motif else 0.0, C.byref(e), st)
+        rc = self.lib.emu_mfe2(self.model, n, _b(seq), _b(cst) if cst else None, _b(motif[0]) if motif else None,
+                               _b(motif[1]) if motif else None, motif[2] if motif else 0.0, C.byref(e), st, 1 if fast else 0)
+        if rc == 1:
+            raise NotImplementedError("fast path declined the sequence")
         if rc:
             raise self._err()
         return e.value, st.raw[:n].decode()

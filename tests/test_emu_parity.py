@@ -32,6 +32,8 @@ def check_fold(oracle, emu, s, cst=None, motif=None):
             assert d2 == pytest.approx(d0, rel=DG_RTOL, abs=1e-12)
             np.testing.assert_allclose(b2, b0, rtol=BP_RTOL, atol=BP_ATOL)
             assert emu.pf(s, cst=cst, motif=motif, fast=True) == d2          # inside-only run
+        # ... and the (min,+) transcription of the same scheme the same optimum and the same traceback
+        assert emu.mfe(s, cst=cst, motif=motif, fast=True) == oracle.mfe(s, cst=cst, motif=motif)
 
 
 def test_reference_sequences(oracle, emu):
