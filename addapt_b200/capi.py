@@ -267,6 +267,8 @@ class Engine:
         n = problem.n
         if thermostat[0] == "fixed":
             kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
+        elif thermostat[0] == "auto":            # (target acceptance rate, training period, initial temperature)
+            kind, ta = 2, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
         else:
             kind, ta = 1, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
         fs = np.zeros((n_traj, n), dtype=np.uint8)
@@ -283,6 +285,8 @@ class Engine:
                    best_seq=None, best_score=None, best_step=None, outcomes=None):
         if thermostat[0] == "fixed":
             kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
+        elif thermostat[0] == "auto":            # (target acceptance rate, training period, initial temperature)
+            kind, ta = 2, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
         else:
             kind, ta = 1, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
         self._check(self.lib.adp_mc_run(self.h, C.byref(problem.c), n_traj, seed, traj_id0, n_steps, kind, ta, _ptr(final_seq),

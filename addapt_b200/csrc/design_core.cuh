@@ -20,6 +20,7 @@ constexpr int kMaxFlank = 64;
 constexpr int kMaxTerms = 16;
 constexpr int kMaxMacro = 8;
 constexpr int kMaxClosure = 16;     // positions changed together by one mutation (a base-pair chain)
+constexpr int kMaxTrain = 512;      // longest training window of the auto-scaling thermostat
 
 struct ScoreProblemDev {
   int32_t n;                         // raw device length
@@ -80,13 +81,13 @@ ADP_HD double add_rn(double a, double b) {
 }
 
 ADP_HD double thermostat_T(int kind, const double* args, int step) {
-  if (kind != 1) return args[0];
+  if (kind != 1) return args[0];      // fixed; the auto-scaling kind is handled by its caller
   const int cycle = (int)args[2];
   return add_rn(mul_rn((args[1] - args[0]) / cycle, (double)(step % cycle)), args[0]);   // sampling.cc:331-338
 }
 
 // Shared-memory bytes a design CTA needs besides the fold working set.
-ADP_HD size_t design_extra_bytes(int n_max) { return 64 + (size_t)(n_max + 16) * 4 + (kMaxVariants + kMaxTerms * kMaxCtx + 8) * sizeof(double); }
+ADP_HD size_t design_extra_bytes(int n_max) { return 96 + (size_t)(n_max + 16) * 4 + (kMaxVariants + kMaxTerms * kMaxCtx + 8 + kMaxTrain) * sizeof(double); }
 
 struct DesignScratch {
   uint8_t* full;     // contextual sequence  [n_max+16]
@@ -96,6 +97,7 @@ struct DesignScratch {
   double* dg;        // [kMaxVariants]
   double* terms;     // [kMaxCtx*kMaxTerms]
   double* bcast;     // [8] broadcast slots
+  double* train;     // [kMaxTrain] score differences the auto-scaling thermostat is trained on
 };
 
 ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
@@ -106,6 +108,7 @@ ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
   d.dg = cv.take<double>(kMaxVariants);
   d.terms = cv.take<double>(kMaxCtx * kMaxTerms);
   d.bcast = cv.take<double>(8);
+  d.train = cv.take<double>(kMaxTrain);
 }
 
 // Score of the raw sequence `raw` (n ASCII bytes, readable by every thread).  Collective; every thread gets
@@ -178,8 +181,38 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
   uint32_t oc0 = 0, oc1 = 0, oc2 = 0, oc3 = 0;
   for (int p = ex.tid(); p < n; p += ex.nthreads()) d.best[p] = d.cur[p];
   ex.sync();
+  // auto-scaling thermostat (kind 2, reference src/sampling.cc:371-401): args = {target acceptance rate, training period,
+  // initial temperature}.  Every step appends the most recent score difference (0 before the first scored proposal) to the
+  // training set; when it holds `period` values, T = max(median / ln(rate), 0) -- "median" being what nth_element leaves at
+  // position size/2 -- and the set is cleared.
+  const int period = thermo_kind == 2 ? (int)thermo_args[1] : 0;
+  int ntrain = 0;
+  double T_auto = thermo_kind == 2 ? thermo_args[2] : 0., last_diff = 0.;
   for (int step = 0; step < n_steps && mv.n_free > 0; step++) {
-    const double T = thermostat_T(thermo_kind, thermo_args, step);
+    double T = thermostat_T(thermo_kind, thermo_args, step);
+    if (thermo_kind == 2) {
+      if (ex.tid() == 0) d.train[ntrain] = last_diff;
+      ntrain++;
+      if (ntrain >= period) {
+        ex.sync();
+        const int mid = ntrain / 2;
+        for (int a = ex.tid(); a < ntrain; a += ex.nthreads()) {      // rank counting: exactly one element has rank mid
+          const double va = d.train[a];
+          int rank = 0;
+          for (int b = 0; b < ntrain; b++) {
+            const double vb = d.train[b];
+            rank += (vb < va) || (vb == va && b < a);
+          }
+          if (rank == mid) d.bcast[0] = va;
+        }
+        ex.sync();
+        const double t = d.bcast[0] / log(thermo_args[0]);
+        T_auto = t > 0. ? t : 0.;
+        ntrain = 0;
+        ex.sync();
+      }
+      T = T_auto;
+    }
     uint32_t r[4];
     philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, 0u, (uint32_t)traj_id, (uint32_t)(traj_id >> 32), r);
     const int slot = (int)(((uint64_t)r[0] * (uint64_t)mv.n_free) >> 32);
@@ -202,6 +235,7 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
     if (!changed) { oc2++; continue; }                                         // ACCEPT_UNCHANGED: not scored
     const double prop_s = score_construct<kFast>(ex, sp, d.prop, d, fold_small, mats, nullptr, dstate);
     const double diff = prop_s - cur_s;
+    last_diff = diff;
     const double crit = exp(diff / T);
     if (crit < u) { oc0++; continue; }                                         // REJECT (NaN compares false: accept)
     if (diff > 0) oc3++; else oc1++;

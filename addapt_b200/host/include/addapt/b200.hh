@@ -81,7 +81,7 @@ struct BatchedTrajectory {
 };
 
 // n independent Monte-Carlo design trajectories on the GPU: UnbiasedMutationMove proposals, Metropolis acceptance,
-// Fixed or Annealing thermostat, all inside one kernel (reference src/sampling.cc:22-107 per trajectory).
+// Fixed, Annealing or AutoScaling thermostat, all inside one kernel (reference src/sampling.cc:22-107 per trajectory).
 // Trajectory t draws from Philox4x32-10 keyed by (seed, first_id + t), so results do not depend on the sharding.
 class BatchedMonteCarlo {
  public:

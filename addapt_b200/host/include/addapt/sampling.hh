@@ -131,6 +131,10 @@ class AutoScalingThermostat : public Thermostat {
   void initial_temperature(double);
   void target_acceptance_rate(double);
   void training_period(unsigned);
+  // read access (not in the reference's header; BatchedMonteCarlo needs it to hand the thermostat to the GPU)
+  double temperature() const { return my_temperature; }
+  double target_acceptance_rate() const { return my_target_acceptance_rate; }
+  unsigned training_period() const { return my_training_period; }
 
  private:
   double my_temperature, my_target_acceptance_rate;

@@ -200,8 +200,13 @@ vector<BatchedTrajectory> BatchedMonteCarlo::apply(DeviceConstPtr device, int n_
     args[0] = anneal->max_temperature();
     args[1] = anneal->min_temperature();
     args[2] = anneal->cycle_len();
+  } else if (auto scaling = std::dynamic_pointer_cast<AutoScalingThermostat>(my_thermostat)) {
+    kind = 2;
+    args[0] = scaling->target_acceptance_rate();
+    args[1] = scaling->training_period();
+    args[2] = scaling->temperature();
   } else {
-    throw string("the batched Monte Carlo kernel supports Fixed and Annealing thermostats");
+    throw string("the batched Monte Carlo kernel supports the Fixed, Annealing and AutoScaling thermostats");
   }
   const size_t n = pk.init_seq.size();
   vector<uint8_t> fin(n * n_traj), best(n * n_traj);

@@ -260,5 +260,9 @@ GPU_TEST_CASE(gpu_batched_mc, "BatchedMonteCarlo: sharding-invariant trajectorie
     for (size_t p = 0; p < tr.final_seq.size(); p++)
       if (std::islower((unsigned char)rhf_6->raw_seq()[p])) CHECK(rhf_6->raw_seq()[p] == tr.final_seq[p]);     // fixed positions stay as given
   }
-  CHECK_THROWS(BatchedMonteCarlo(fx, 10, make_shared<AutoScalingThermostat>()).apply(rhf_6, 1, 0));
+  // the auto-scaling thermostat runs on the device too; an unknown thermostat class is refused
+  auto scaled = BatchedMonteCarlo(fx, 60, make_shared<AutoScalingThermostat>(0.5, 20, 1.0)).apply(rhf_6, 2, 7);
+  CHECK(scaled.size() == 2 && scaled[0].best_score >= start - 1e-12);
+  class OddThermostat : public Thermostat { double adjust(MonteCarloStep const&) { return 1; } };
+  CHECK_THROWS(BatchedMonteCarlo(fx, 10, make_shared<OddThermostat>()).apply(rhf_6, 1, 0));
 }

@@ -105,8 +105,27 @@ int orc_mc_run(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t
   memcpy(best, cur, n + 1);
   int bstep = -1, rc = 0;
   uint32_t oc[4] = {0, 0, 0, 0};
+  /* auto-scaling thermostat (reference src/sampling.cc:371-401): every step appends the most recent score difference to a
+   * training set; once it holds `period` values the temperature becomes max(median / ln(rate), 0) and the set is cleared */
+  int period = tk == 2 ? (int)ta[1] : 0, ntrain = 0;
+  double *train = tk == 2 ? (double *)malloc(sizeof(double) * (period > 0 ? period : 1)) : NULL;
+  double T_auto = tk == 2 ? ta[2] : 0., last_diff = 0.;
   for (int i = 0; i < n_steps && nfree > 0; i++) {
     double T = (tk == 1) ? ((ta[1] - ta[0]) / (int)ta[2]) * (i % (int)ta[2]) + ta[0] : ta[0];
+    if (tk == 2) {
+      train[ntrain++] = last_diff;
+      if (ntrain >= period) {
+        int mid = ntrain / 2;
+        /* the value nth_element leaves at position mid = the mid-th smallest */
+        for (int a = 0; a < ntrain; a++) {
+          int rank = 0;
+          for (int b = 0; b < ntrain; b++) rank += (train[b] < train[a]) || (train[b] == train[a] && b < a);
+          if (rank == mid) { double t = train[a] / log(ta[0]); T_auto = t > 0. ? t : 0.; break; }
+        }
+        ntrain = 0;
+      }
+      T = T_auto;
+    }
     uint32_t ctr[4] = {(uint32_t)i, 0u, (uint32_t)traj, (uint32_t)(traj >> 32)}, r[4];
     orc_philox4x32((uint32_t)seed, (uint32_t)(seed >> 32), ctr, r);
     int pos = freep[(uint32_t)(((uint64_t)r[0] * (uint64_t)nfree) >> 32)];
@@ -120,6 +139,7 @@ int orc_mc_run(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t
     if (!memcmp(prop, cur, n)) outcome = 2;
     else {
       double ps = orc_score(M, P, prop, float_dg, NULL), d = ps - cur_s, crit = exp(d / T);
+      last_diff = d;
       if (crit < u) outcome = 0;
       else {
         outcome = (d > 0) ? 3 : 1;
@@ -136,6 +156,6 @@ int orc_mc_run(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t
   if (best_score) *best_score = bs;
   if (best_step) *best_step = bstep;
   if (outcomes) memcpy(outcomes, oc, sizeof oc);
-  free(freep); free(cur); free(prop); free(best); free(done);
+  free(freep); free(cur); free(prop); free(best); free(done); free(train);
   return rc;
 }

@@ -167,6 +167,8 @@ class Oracle:
         n = P.n
         if thermostat[0] == "fixed":
             tk, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
+        elif thermostat[0] == "auto":            # (target acceptance rate, training period, initial temperature)
+            tk, ta = 2, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
         else:
             tk, ta = 1, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
         fs, bs = C.create_string_buffer(n + 1), C.create_string_buffer(n + 1)

@@ -188,7 +188,7 @@ int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, 
     SerialExec ex;
     std::memcpy(d.cur, pr->init_seq, pr->n);
     McResult res;
-    double ta[3] = {targs[0], kind == 1 ? targs[1] : 0., kind == 1 ? targs[2] : 1.};
+    double ta[3] = {targs[0], kind >= 1 ? targs[1] : 0., kind >= 1 ? targs[2] : 1.};
     if (fast) mc_trajectory<true>(ex, cp.sp, mv[0], seed, traj_id, n_steps, kind, ta, d, small.data(), mats.data(), &res, dstate.data());
     else mc_trajectory<false>(ex, cp.sp, mv[0], seed, traj_id, n_steps, kind, ta, d, small.data(), mats.data(), &res);
     std::memcpy(final_seq, d.cur, pr->n);

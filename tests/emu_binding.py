@@ -97,6 +97,8 @@ class Emu:
         n = problem.n
         if thermostat[0] == "fixed":
             kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
+        elif thermostat[0] == "auto":            # (target acceptance rate, training period, initial temperature)
+            kind, ta = 2, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
         else:
             kind, ta = 1, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
         fs, bs = C.create_string_buffer(n + 1), C.create_string_buffer(n + 1)

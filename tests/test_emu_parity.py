@@ -141,7 +141,8 @@ def test_score_with_contexts(oracle, emu):
 
 def test_monte_carlo_trajectory(oracle, emu):
     pr = cases.rhf6_problem()
-    for seed, traj, thermo in ((2016, 7, ("annealing", 5.0, 0.0, 300)), (1, 123456789012, ("fixed", 1.0)), (3, 0, ("annealing", 2.0, 0.0, 7))):
+    for seed, traj, thermo in ((2016, 7, ("annealing", 5.0, 0.0, 300)), (1, 123456789012, ("fixed", 1.0)), (3, 0, ("annealing", 2.0, 0.0, 7)),
+                               (4, 5, ("auto", 0.5, 6, 1.0)), (9, 11, ("auto", 0.3, 1, 0.25))):
         a = oracle.mc_run(pr.as_oracle_dict(), seed, traj, 30, thermostat=thermo)
         for fast in (False, True):
             b = emu.mc_run(pr, seed, traj, 30, thermostat=thermo, fast=fast)

@@ -180,7 +180,7 @@ def test_score_and_contexts(oracle, engine):
 def test_monte_carlo_matches_oracle_step_for_step(oracle, engine):
     pr = cases.rhf6_problem()
     n_traj, steps = 6, 40
-    for thermo in (("annealing", 5.0, 0.0, 300), ("fixed", 1.0)):
+    for thermo in (("annealing", 5.0, 0.0, 300), ("fixed", 1.0), ("auto", 0.5, 8, 1.0)):
         r = engine.mc_run(pr, n_traj, 2016, steps, thermostat=thermo, traj_id0=1000)
         for t in range(n_traj):
             a = oracle.mc_run(pr.as_oracle_dict(), 2016, 1000 + t, steps, thermostat=thermo)
