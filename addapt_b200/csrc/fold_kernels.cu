@@ -1,6 +1,8 @@
 // sm_100a kernels for batched folds: one construct per CTA, persistent CTAs striding over the job list.
 // The recursions live in pf_core.cuh / mfe_core.cuh; this file binds them to a CTA, shared memory and the
 // batch layout.  No tensor cores (the recursions are not dense contractions), no library calls.
+#include <cstdlib>
+
 #include "fold_jobs.cuh"
 #include "kernels.h"
 
@@ -249,6 +251,10 @@ LaunchPlan plan_pf_fast(const DeviceInfo& d, int n, int jobs) {
   size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);   // 1 KB reserved per resident CTA
   size_t by_threads = p.threads == 256 ? 2 : 1;            // __launch_bounds__ of pf_fast_kernel
   size_t occ = per_sm < by_threads ? per_sm : by_threads;
+  if (const char* cap = std::getenv("ADDAPT_B200_MAX_CTAS_PER_SM")) {   // experiments only
+    const size_t c = (size_t)std::atoi(cap);
+    if (c >= 1 && c < occ) occ = c;
+  }
   if (occ < 1) occ = 1;
   long grid = (long)d.sm_count * (long)occ;
   if (grid > jobs) grid = jobs;
