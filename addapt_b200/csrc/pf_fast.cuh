@@ -1,4 +1,4 @@
-// Fast McCaskill inside / outside pass, one construct per CTA (ACGU-only sequences, n <= fast_max_len(threads)).
+// Fast McCaskill inside / outside pass, one construct per CTA (ACGU/T-only sequences, n <= kFastMaxN).
 // Same ensemble as pf_core.cuh (the general path) and as vrna_pf in the reference (src/scoring.cc:43,58,65);
 // what differs is how the work is organised for the SM:
 //
@@ -15,11 +15,16 @@
 //    recursion costs no shared memory and no barrier.  The outside pass runs the mirrored recursion over the
 //    enclosing pairs, (k,l) -> (k-1,l+1).  Level parity is a compile-time constant of the code path, so the loop
 //    size s is an immediate and the size-dependent factors come from the constant bank.
+//    Levels that are off for a thread (no room, or closed by the hard constraint) read an always-zero word instead, so
+//    the recursion is branch-free and every lane of a warp executes the same instructions.
+//  * Qb (and, in the outside pass, the outside weight) is stored PREMULTIPLIED by the generic mismatch factor of its
+//    pair, so the two border candidates of every level are single loads; the other readers multiply by a ratio from a
+//    16x16 table (1/FI, terminal-AU/FI, F1n/FI, FM/FI).
 //  * The candidates on the loop's axes (bulges, 1xn loops: 112 per cell) are four 1-D filters; the two that run
 //    down a column read a per-column vector premultiplied once, the two that run along a row are evaluated by the
 //    cell's lanes.  The 9 corner candidates (stack, bulge-1, 1x1, 1x2, 2x2, 2x3) use the full tables.
-//  * All per-pair mismatch factors come from 16x16 tables indexed by two one-byte position codes
-//    (nucleotide + 3' neighbour, nucleotide + 5' neighbour), staged once per CTA.
+//  * All per-pair factors come from 16x16 tables indexed by two one-byte position codes
+//    (nucleotide + 3' neighbour, nucleotide + 5' neighbour), staged once per job.
 //  * Only cells that can pair are evaluated: each column compacts them into a list, and a power-of-two lane group
 //    per cell (sized so the list fills the CTA) splits the cell's terms and reduces with shuffles.
 //  * Two barriers per column: the sparse per-cell phase alone, then everything that is independent of it (Qm of

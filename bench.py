@@ -210,7 +210,12 @@ def main():
     from addapt_b200.capi import Problem
 
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = os.environ.get("ADDAPT_NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout: one JSON line only
+    # stdout carries ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/WARN/INFO, so logging is off
+    # unless asked for explicitly, and then it goes to stderr
+    os.environ.pop("NCCL_DEBUG", None)
+    if os.environ.get("ADDAPT_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["ADDAPT_NCCL_DEBUG"]
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = addapt_b200.Engine(local)          # raises without the CUDA library / device: no fallback
