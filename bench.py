@@ -160,7 +160,7 @@ def run_reference(args, rank):
     orc.pf_batch(rows[:2 * cores], motif=THEO, bppm=True, threads=cores)
     rate = 2 * cores / (time.perf_counter() - t0)
     budget = 120.0 / max(1, args.steps + args.warmup)            # whole run <= ~2 minutes
-    m = int(max(cores, min(len(rows), rate * min(budget, 15.0))))
+    m = int(max(cores, min(len(rows), rate * min(budget, float(os.environ.get("ADDAPT_BENCH_REF_SECONDS", "15"))))))
     m -= m % cores
     times = []
     for s in range(args.warmup + args.steps):
