@@ -256,7 +256,7 @@ ADP_HD double qm_row_terms(const double* qm, const double* qm1, const double* eM
 
 // ---------------------------------------------------------------------------------------------------
 // inside pass.  Returns Z = Q(1,n) (scaled) on every thread.
-// vector roles: 0/1 Qm1 columns by parity, 2 exterior terms of the listed cells, 3 xA (Qb * terminal factor, column
+// vector roles: 0/1 Qm1 columns by parity, 2 and 7 exterior terms per row by column parity, 3 xA (Qb * terminal factor, column
 // j-1), 4/5 x1n (Qb * 1xn mismatch, by column parity), 6/7/8 xI (Qb * generic mismatch, by column mod 3), 9 q1,
 // 10 eMLb powers, 11/12 generic-loop sums per level parity.
 template <bool kCst, class E>
@@ -275,7 +275,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     if (k < 10 * ld || k >= 11 * ld) w.vbase[k] = 0.;
   double* const q1 = w.vecp(9);
   const double* const eMLbS = w.vecp(10);
-  double* const ext = w.vecp(2);
   double* const xA = w.vecp(3);
   double* const gen0 = w.vecp(11);
   double* const gen1 = w.vecp(12);
@@ -339,8 +338,10 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       if (mem_state)
         for (int q = 0; q < kFastLevels; q++) w.dstate[(size_t)task * kFastLevels + q] = d[q];
     }
+    double* ext_n = w.vecp((jn & 1) ? 7 : 2);      // exterior terms by ROW (summed in row order: results do not depend on list order)
     for (int r = tid; r < nr; r += nt) {
       qm1_cur[r + 1] = cuj ? qm1_prev[r + 1] * eb1 : 0.;
+      ext_n[r + 1] = 0.;
       if (kCst ? allowed_type(c, r + 1, jn) != 0 : pair_type(c.S[r + 1], c.S[jn]) != 0) w.cells[ex.atomic_inc(counter)] = (uint16_t)(r + 1);
     }
   };
@@ -352,6 +353,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     const bool cuj = !kCst || can_unpair(c, j);
     const double* qm1_prev = w.vecp((j - 1) & 1);
     double* qm1_cur = w.vecp(j & 1);
+    double* ext = w.vecp((j & 1) ? 7 : 2);
     const int m = w.counter[j & 1];
     // ---- interval 1: Qb(i,j) for the listed cells, a lane group per cell
     {
@@ -445,7 +447,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         if (valid && sub == 0) {
           qb[t4(i, j)] = (i > 1 && j < n) ? acc * H.FI[(cn[j] << 4) | cp[i]] : acc;     // stored premultiplied
           qm1_cur[i] += acc * fast_stem_ml(c, H, G, w, type, i, j);
-          ext[slot] = acc * fast_stem_ext(c, G, type, i, j) * q1[i - 1];
+          ext[i] = acc * fast_stem_ext(c, G, type, i, j) * q1[i - 1];
         }
       }
     }
@@ -482,7 +484,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       }
       if (ex.warp() == 0) {
         double e = 0.;
-        for (int s = ex.lane(); s < m; s += E::kWarp) e += ext[s];
+        for (int s = 1 + ex.lane(); s <= nr; s += E::kWarp) e += ext[s];
         e = ex.warp_sum(e);
         if (ex.lane() == 0) q1[j] = (cuj ? q1[j - 1] * s1 : 0.) + e;
       }

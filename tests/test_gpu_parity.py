@@ -164,6 +164,41 @@ def test_fold_eval_matches_oracle(oracle, engine):
                 assert pr[b, c, k] == pytest.approx(want, rel=BP_RTOL, abs=BP_ATOL)
 
 
+def test_results_are_bitwise_reproducible(engine):
+    """compute-sanitizer is not available on this pool, so data races are hunted the other way round: every result must be
+    bit-identical from run to run, whatever the batch composition (which CTA folds which construct, in which order the
+    cell lists are compacted) and whichever co-resident CTA shares the SM"""
+    rng = np.random.Generator(np.random.PCG64(11))
+    seqs = cases.templated_designs(600, 21, n=100)
+    q = [(0, 29), (47, 79), (50, 76), (33, 73)]
+    dg0, pr0, _ = engine.fold_eval(seqs, cases.THEO, queries=q)
+    dg1, pr1, _ = engine.fold_eval(seqs, cases.THEO, queries=q)
+    assert np.array_equal(dg0, dg1) and np.array_equal(pr0, pr1)
+    perm = rng.permutation(len(seqs))
+    dg2, pr2, _ = engine.fold_eval([seqs[k] for k in perm], cases.THEO, queries=q)
+    assert np.array_equal(dg2, dg0[perm]) and np.array_equal(pr2, pr0[perm])
+    sub = perm[:37]
+    dg3, _, full3 = engine.fold_eval([seqs[k] for k in sub], cases.THEO, queries=q, full=True)
+    assert np.array_equal(dg3, dg0[sub])
+    _, _, full4 = engine.fold_eval([seqs[k] for k in sub], cases.THEO, queries=q, full=True)
+    assert np.array_equal(full3, full4)
+    cst = cases.RHF6_ACTIVE[:100]
+    a = engine.pf(seqs, cst=cst, motif=cases.THEO)
+    b = engine.pf([seqs[k] for k in perm], cst=cst, motif=cases.THEO)
+    assert np.array_equal(b, a[perm])
+    long_seqs = cases.random_seqs(40, 300, 5)              # level sums in global scratch, matrices in L2
+    assert np.array_equal(engine.pf(long_seqs), engine.pf(long_seqs))
+    pr = cases.rhf6_problem()
+    designs = cases.templated_designs(300, 22, n=102)
+    assert np.array_equal(engine.score(pr, designs), engine.score(pr, designs))
+    e0, s0 = engine.mfe(seqs)
+    e1, s1 = engine.mfe([seqs[k] for k in perm])
+    assert np.array_equal(e1, e0[perm]) and s1 == [s0[k] for k in perm]
+    r0 = engine.mc_run(pr, 48, 7, 25)
+    r1 = engine.mc_run(pr, 48, 7, 25)
+    assert r0["final_seq"] == r1["final_seq"] and np.array_equal(r0["best_score"], r1["best_score"])
+
+
 def test_score_and_contexts(oracle, engine):
     designs = cases.templated_designs(24, 4, n=102)
     for float_dg in (False, True):
