@@ -86,8 +86,9 @@ ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats)
 // The fast path (pf_fast.cuh) for the same job.  `small`: fast_small_bytes(n) of shared memory; `mats`:
 // fast_matrix_doubles(n) doubles (shared or global); `dstate`: host emulation only.  Returns false (on every
 // thread, nothing written) when the sequence holds a letter outside ACGU/T -- the caller then uses run_pf_job.
+// `qm_ext` (optional): put Qm there (global scratch, t4_count(n)+2 doubles) instead of behind Qb in `mats`.
 template <class E>
-ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* mats, double* dstate = nullptr) {
+ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* mats, double* dstate = nullptr, double* qm_ext = nullptr) {
   const int n = job.n;
   Carver cv(small);
   PfHot* H = cv.take<PfHot>(1);
@@ -102,7 +103,7 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   w.cells = cv.take<uint16_t>(w.ld);
   w.counter = cv.take<int>(4);
   w.qb = mats;
-  w.qm = mats + t4_count(n) + 1;
+  w.qm = qm_ext ? qm_ext : mats + t4_count(n) + 1;
   w.scaleG = job.T->scale;
   w.dstate = dstate;
   c.has_cst = job.cst != nullptr;

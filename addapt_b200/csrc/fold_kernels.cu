@@ -8,6 +8,8 @@
 
 namespace adp {
 
+constexpr bool kQmGlobalDefault = false;     // see plan_pf_fast
+
 extern __shared__ __align__(16) unsigned char adp_smem[];
 
 template <int G, bool kSmemMats>
@@ -97,28 +99,32 @@ __device__ __forceinline__ PfJob make_pf_job(const PfBatchArgs& a, int jid) {
 }
 
 // Fast path: one construct per CTA, level sums of the generic interior loops in registers (pf_fast.cuh).
-// kThreads = 256 serves n <= 128 with two CTAs per SM at 100 nt; 512 serves n <= 256.
-template <int kThreads, bool kSmemMats>
-__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) pf_fast_kernel(const PfBatchArgs a) {
+// kThreads = 256 serves n <= 128 with two CTAs per SM at 100 nt; 512 serves longer constructs.
+// kQmGlobal: Qb stays in shared memory, Qm moves to the CTA's slab of (L2-resident) global scratch, which makes room for a
+// third construct per SM at 100 nt (85 registers per thread).
+template <int kThreads, bool kSmemMats, bool kQmGlobal>
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? (kQmGlobal ? 3 : 2) : 1) pf_fast_kernel(const PfBatchArgs a) {
   CtaExec<1> ex;
   const int n = a.n;
   const int jobs = a.B * a.V;
   void* small = adp_smem;
   double* mats;
+  double* qm_ext = nullptr;
+  size_t gused = 0;                  // doubles of this CTA's global slab already handed out
+  double* slab = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
   if (kSmemMats) {
     size_t off = (fast_small_bytes(n) + 15) & ~(size_t)15;
     mats = reinterpret_cast<double*>(adp_smem + off);
+    if (kQmGlobal) { qm_ext = slab; gused = t4_count(n) + 2; }
   } else {
-    mats = a.gmats + (size_t)blockIdx.x * a.gmat_stride;
+    mats = slab;
+    gused = fast_matrix_doubles(n);
   }
-  // constructs longer than threads/2 have more anti-diagonals than threads: their level sums live in the CTA's slab of
-  // global scratch (behind the matrices when those are global too)
-  double* dstate = nullptr;
-  if (n > fast_max_len(kThreads))
-    dstate = a.gmats + (size_t)blockIdx.x * a.gmat_stride + (kSmemMats ? 0 : fast_matrix_doubles(n));
+  // constructs longer than threads/2 have more anti-diagonals than threads: their level sums live in global scratch too
+  double* dstate = n > fast_max_len(kThreads) ? slab + gused : nullptr;
   for (int jid = blockIdx.x; jid < jobs; jid += gridDim.x) {
     const PfJob job = make_pf_job(a, jid);
-    const bool done = run_pf_job_fast(ex, job, small, mats, dstate);
+    const bool done = run_pf_job_fast(ex, job, small, mats, dstate, qm_ext);
     if (!done && threadIdx.x == 0) { a.redo[jid] = 1; atomicAdd(a.redo + jobs, 1); }
     __syncthreads();   // the next job reuses the working set
   }
@@ -238,18 +244,30 @@ cudaError_t launch_pf(const PfBatchArgs& a, const LaunchPlan& p, cudaStream_t st
 
 LaunchPlan plan_pf_fast(const DeviceInfo& d, int n, int jobs) {
   LaunchPlan p{};
-  // 256 threads keep the level sums of n <= 128 in registers with two CTAs per SM; 512 threads serve n <= 256 the same way and
-  // longer constructs (up to kFastMaxN) with the sums in global scratch
+  // 256 threads keep the level sums of n <= 128 in registers; 512 threads serve n <= 256 the same way and longer constructs
+  // (up to kFastMaxN) with the sums in global scratch
   p.threads = n <= fast_max_len(256) ? 256 : n <= kFastMaxN ? 512 : 0;
   if (!p.threads) return p;
   p.group = 1;
   const size_t small_al = (fast_small_bytes(n) + 15) & ~(size_t)15;
   const size_t mats_bytes = fast_matrix_doubles(n) * sizeof(double);
+  const size_t qb_bytes = (t4_count(n) + 2) * sizeof(double);
   p.mats_in_smem = small_al + mats_bytes <= d.smem_optin;
   p.smem_bytes = p.mats_in_smem ? small_al + mats_bytes : small_al;
-  p.gmat_stride = (p.mats_in_smem ? 0 : fast_matrix_doubles(n)) + (n > fast_max_len(p.threads) ? fast_state_doubles(n) : 0);
-  size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);   // 1 KB reserved per resident CTA
+  size_t gdoubles = p.mats_in_smem ? 0 : fast_matrix_doubles(n);
   size_t by_threads = p.threads == 256 ? 2 : 1;            // __launch_bounds__ of pf_fast_kernel
+  // Qm in global scratch when that lets a third construct share the SM (group = 3 selects that kernel variant)
+  const char* qmg = std::getenv("ADDAPT_B200_QM_GLOBAL");
+  const bool want_qmg = qmg ? std::atoi(qmg) != 0 : kQmGlobalDefault;
+  if (want_qmg && p.threads == 256 && p.mats_in_smem && d.smem_per_sm / (p.smem_bytes + 1024) < 3 &&
+      d.smem_per_sm / (small_al + qb_bytes + 1024) >= 3) {
+    p.group = 3;
+    p.smem_bytes = small_al + qb_bytes;
+    gdoubles = t4_count(n) + 2;
+    by_threads = 3;
+  }
+  p.gmat_stride = gdoubles + (n > fast_max_len(p.threads) ? fast_state_doubles(n) : 0);
+  size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);   // 1 KB reserved per resident CTA
   size_t occ = per_sm < by_threads ? per_sm : by_threads;
   if (const char* cap = std::getenv("ADDAPT_B200_MAX_CTAS_PER_SM")) {   // experiments only
     const size_t c = (size_t)std::atoi(cap);
@@ -269,11 +287,12 @@ cudaError_t launch_pf_fast(const PfBatchArgs& a, const LaunchPlan& p, const PfTa
   cudaError_t ce = cudaMemcpyToSymbolAsync(c_fast_const, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
   if (ce != cudaSuccess) return ce;
   if (p.threads == 256) {
-    if (p.mats_in_smem) ADP_LAUNCH((pf_fast_kernel<256, true>), a);
-    ADP_LAUNCH((pf_fast_kernel<256, false>), a);
+    if (p.group == 3) ADP_LAUNCH((pf_fast_kernel<256, true, true>), a);
+    if (p.mats_in_smem) ADP_LAUNCH((pf_fast_kernel<256, true, false>), a);
+    ADP_LAUNCH((pf_fast_kernel<256, false, false>), a);
   }
-  if (p.mats_in_smem) ADP_LAUNCH((pf_fast_kernel<512, true>), a);
-  ADP_LAUNCH((pf_fast_kernel<512, false>), a);
+  if (p.mats_in_smem) ADP_LAUNCH((pf_fast_kernel<512, true, false>), a);
+  ADP_LAUNCH((pf_fast_kernel<512, false, false>), a);
 }
 
 LaunchPlan plan_mfe_fast(const DeviceInfo& d, int n, int jobs) {
