@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 256 ? (kQmGlobal ? 3 : 2
 
 // Fast MFE path (mfe_fast.cuh): int32 matrices are half the size of the PF ones, so up to four constructs share an SM.
 template <int kThreads, bool kSmemMats>
-__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 3 : 1) mfe_fast_kernel(const MfeBatchArgs a) {
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 4 : 1) mfe_fast_kernel(const MfeBatchArgs a) {
   CtaExec<1> ex;
   const int n = a.n;
   void* small = adp_smem;
@@ -306,7 +306,7 @@ LaunchPlan plan_mfe_fast(const DeviceInfo& d, int n, int jobs) {
   p.smem_bytes = p.mats_in_smem ? small_al + mats_bytes : small_al;
   p.gmat_stride = (p.mats_in_smem ? 0 : mfe_fast_matrix_ints(n)) + (n > fast_max_len(p.threads) ? fast_state_doubles(n) : 0);
   size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);
-  size_t by_threads = p.threads == 256 ? 3 : 1;            // __launch_bounds__ of mfe_fast_kernel
+  size_t by_threads = p.threads == 256 ? 4 : 1;            // __launch_bounds__ of mfe_fast_kernel
   size_t occ = per_sm < by_threads ? per_sm : by_threads;
   if (occ < 1) occ = 1;
   long grid = (long)d.sm_count * (long)occ;
