@@ -122,6 +122,18 @@ def test_general_kernels_and_mixed_alphabet(oracle, engine):
         engine.set_general_only(0)
 
 
+def test_long_constructs_with_constraints_and_motif(oracle, engine):
+    """the 512-thread fast kernels beyond 128 nt (level sums in registers up to 256 nt, in global scratch above; matrices in
+    shared memory up to ~150 nt, in L2 above), with a hard constraint and the ligand motif"""
+    rng = np.random.Generator(np.random.PCG64(17))
+    for n in (140, 190, 270, 320):
+        a, b = n // 3, n - n // 3 - len(cases.THEO[0])
+        s = cases.random_seqs(1, a, n)[0] + cases.THEO[0] + cases.random_seqs(1, b, n + 1)[0]
+        cst = cases.random_constraint(oracle, s, rng)
+        check_batch(oracle, engine, [s, s], cst=cst, motif=cases.THEO)
+        check_batch(oracle, engine, [s], motif=cases.THEO)
+
+
 def test_constraints_and_motif(oracle, engine):
     rng = np.random.Generator(np.random.PCG64(7))
     seqs = cases.templated_designs(16, 8, n=100)
