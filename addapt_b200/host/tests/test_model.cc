@@ -1,95 +1,102 @@
-// The reference's tests/test_model.cc cases, run against the facade's Device / Aptamer / Context.
+// Device / Aptamer / Context behaviour pinned by the reference's tests/test_model.cc, restated as tables.
 #include "addapt/model.hh"
 #include "check.hh"
 
 using namespace addapt;
 
-TEST_CASE(model_device, "Device: sequence, indexing, macrostates, copy/assign (reference tests/test_model.cc:8-41)") {
-  Device dummy("ACGU");
-  CHECK(dummy.seq() == "ACGU");
-  CHECK(dummy.len() == 4);
-  const char* fwd = "ACGU";
-  for (int k = 0; k < 4; k++) CHECK(dummy.seq(k) == fwd[k]);
-  CHECK_THROWS(dummy.seq(4));
-  for (int k = 1; k <= 4; k++) CHECK(dummy.seq(-k) == fwd[4 - k]);
-  CHECK_THROWS(dummy.seq(-5));
-
-  dummy.add_macrostate("a", "....");
-  dummy.add_macrostate("b", "(())");
-  CHECK(dummy.macrostate("a") == "....");
-  CHECK(dummy.macrostate("b") == "(())");
-  CHECK_THROWS(dummy.macrostate("missing"));
-  CHECK_THROWS(dummy.add_macrostate("short", "..."));
-
-  DevicePtr twin = dummy.copy();
-  CHECK(twin->seq() == "ACGU");
-  CHECK(twin->macrostate("a") == "....");
-  CHECK(twin->macrostate("b") == "(())");
-
-  Device other("nnnn");
-  CHECK(other.seq() == "nnnn");
-  other.assign(twin);
-  CHECK(other.seq() == "ACGU");
-  CHECK(other.macrostate("b") == "(())");
-}
-
-TEST_CASE(model_context, "Device with a context (reference tests/test_model.cc:43-89)") {
-  Device dummy("C");
-  dummy.add_macrostate("bp", "x");
-  CHECK(dummy.context()->before() == "");
-  CHECK(dummy.context()->after() == "");
-
-  dummy.context(make_shared<Context>("A", "GU"));
-  CHECK(dummy.len() == 4);
-  CHECK(dummy.seq() == "ACGU");
-  CHECK(dummy.seq(0) == 'A');
-  CHECK(dummy.seq(3) == 'U');
-  CHECK(dummy.raw_len() == 1);
-  CHECK(dummy.raw_seq() == "C");
-  CHECK(dummy.raw_seq(0) == 'C');
-  CHECK(dummy.macrostate("bp") == ".x..");
-  CHECK(dummy.context()->before() == "A");
-  CHECK(dummy.context()->after() == "GU");
-  for (auto ms : dummy.macrostates()) { CHECK(ms.first == "bp"); CHECK(ms.second == ".x.."); }
-
-  dummy.remove_context();
-  CHECK(dummy.len() == 1);
-  CHECK(dummy.seq() == "C");
-  CHECK(dummy.macrostate("bp") == "x");
-  for (auto ms : dummy.macrostates()) { CHECK(ms.first == "bp"); CHECK(ms.second == "x"); }
-}
-
-TEST_CASE(model_mutate, "Device::mutate (reference tests/test_model.cc:91-112)") {
-  {
-    Device d("AAAA");
-    const char* want[] = {"UAAA", "UUAA", "UUUA", "UUUU"};
-    for (int k = 0; k < 4; k++) { d.mutate(k, 'U'); CHECK(d.seq() == want[k]); }
+namespace {
+void expect_macrostates(Device const& d, string const& name, string const& cst) {
+  int seen = 0;
+  for (auto const& ms : d.macrostates()) {
+    seen++;
+    CHECK(ms.first == name);
+    CHECK(ms.second == cst);
   }
-  {
+  CHECK(seen == 1);
+}
+}  // namespace
+
+TEST_CASE(model_device, "Device: sequence, python-style indexing, macrostates, copy / assign (reference tests/test_model.cc:8-41)") {
+  Device four("ACGU");
+  CHECK(four.seq() == "ACGU" && four.len() == 4 && four.raw_len() == 4);
+  const string letters = "ACGU";
+  for (int k = 0; k < 4; k++) {
+    CHECK(four.seq(k) == letters[k]);            // from the front
+    CHECK(four.seq(k - 4) == letters[k]);        // -4 .. -1 from the back
+  }
+  for (int bad : {4, -5, 17}) CHECK_THROWS(four.seq(bad));
+
+  const vector<pair<string, string>> states = {{"a", "...."}, {"b", "(())"}};
+  for (auto const& st : states) four.add_macrostate(st.first, st.second);
+  CHECK_THROWS(four.macrostate("missing"));
+  CHECK_THROWS(four.add_macrostate("short", "..."));     // length must match the raw sequence
+
+  DevicePtr twin = four.copy();
+  Device blank("nnnn");
+  CHECK(blank.seq() == "nnnn");
+  blank.assign(twin);
+  for (Device const* d : {static_cast<Device const*>(&four), static_cast<Device const*>(twin.get()), static_cast<Device const*>(&blank)}) {
+    CHECK(d->seq() == "ACGU");
+    for (auto const& st : states) CHECK(d->macrostate(st.first) == st.second);
+  }
+  twin->mutate(0, 'G');                                    // copies are deep
+  CHECK(four.seq() == "ACGU" && twin->seq() == "GCGU");
+}
+
+TEST_CASE(model_context, "Device embedded in a context and released again (reference tests/test_model.cc:43-89)") {
+  Device d("C");
+  d.add_macrostate("bp", "x");
+  CHECK(d.context()->before().empty() && d.context()->after().empty());
+
+  d.context(make_shared<Context>("A", "GU"));
+  CHECK(d.len() == 4 && d.seq() == "ACGU");
+  CHECK(d.seq(0) == 'A' && d.seq(1) == 'C' && d.seq(2) == 'G' && d.seq(3) == 'U');
+  CHECK(d.raw_len() == 1 && d.raw_seq() == "C" && d.raw_seq(0) == 'C');      // the raw view ignores the context
+  CHECK(d.macrostate("bp") == ".x..");                                      // flanks are padded with '.'
+  CHECK(d.context()->before() == "A" && d.context()->after() == "GU");
+  expect_macrostates(d, "bp", ".x..");
+
+  d.remove_context();
+  CHECK(d.len() == 1 && d.seq() == "C" && d.seq(0) == 'C');
+  CHECK(d.raw_len() == 1 && d.raw_seq() == "C" && d.raw_seq(0) == 'C');
+  CHECK(d.macrostate("bp") == "x");
+  CHECK(d.context()->before().empty() && d.context()->after().empty());
+  expect_macrostates(d, "bp", "x");
+}
+
+TEST_CASE(model_mutate, "Device::mutate indexes the raw sequence, either end (reference tests/test_model.cc:91-112)") {
+  struct Walk { int first, step; vector<string> expect; };
+  const vector<Walk> walks = {{0, 1, {"UAAA", "UUAA", "UUUA", "UUUU"}}, {-1, -1, {"AAAU", "AAUU", "AUUU", "UUUU"}}};
+  for (Walk const& wk : walks) {
     Device d("AAAA");
-    const char* want[] = {"AAAU", "AAUU", "AUUU", "UUUU"};
-    for (int k = 1; k <= 4; k++) { d.mutate(-k, 'U'); CHECK(d.seq() == want[k - 1]); }
+    int at = wk.first;
+    for (string const& want : wk.expect) {
+      d.mutate(at, 'U');
+      CHECK(d.seq() == want);
+      at += wk.step;
+    }
   }
   Device d("AAAA");
-  CHECK_THROWS(d.mutate(4, 'U'));
-  CHECK_THROWS(d.mutate(-5, 'U'));
+  for (int bad : {4, -5}) CHECK_THROWS(d.mutate(bad, 'U'));
+  CHECK(d.seq() == "AAAA");
 }
 
 TEST_CASE(model_aptamer, "Aptamer accessors (reference tests/test_model.cc:114-123)") {
-  Aptamer theo("GAUACCAGCCGAAAGGCCCUUGGCAGC", "(...((.(((....)))....))...)", 0.320);
-  CHECK(theo.seq() == "GAUACCAGCCGAAAGGCCCUUGGCAGC");
-  CHECK(theo.fold() == "(...((.(((....)))....))...)");
-  CHECK(theo.affinity() == 0.320);
+  const string seq = "GAUACCAGCCGAAAGGCCCUUGGCAGC", fold = "(...((.(((....)))....))...)";
+  Aptamer theo(seq, fold, 0.320);
+  CHECK(theo.seq() == seq && theo.fold() == fold && theo.affinity() == 0.320);
 }
 
 TEST_CASE(utils_index, "normalize_index / normalize_range (reference src/utils.cc:5-40)") {
-  CHECK(normalize_index("ACGU", 0, IndexEnum::ITEM) == 0);
-  CHECK(normalize_index("ACGU", -1, IndexEnum::ITEM) == 3);
-  CHECK(normalize_index("ACGU", 4, IndexEnum::BETWEEN) == 4);
-  CHECK(normalize_index("ACGU", -1, IndexEnum::BETWEEN) == 4);
-  CHECK_THROWS(normalize_index("ACGU", 4, IndexEnum::ITEM));
-  CHECK_THROWS(normalize_index("ACGU", 5, IndexEnum::BETWEEN));
-  auto r = normalize_range("ACGU", -1, 1, IndexEnum::ITEM);
-  CHECK(r.first == 1);
-  CHECK(r.second == 3);
+  struct Row { int index; IndexEnum kind; int expect; };     // expect < 0: throws
+  const vector<Row> rows = {{0, IndexEnum::ITEM, 0}, {3, IndexEnum::ITEM, 3}, {-1, IndexEnum::ITEM, 3}, {-4, IndexEnum::ITEM, 0},
+                            {4, IndexEnum::ITEM, -1}, {-5, IndexEnum::ITEM, -1}, {4, IndexEnum::BETWEEN, 4}, {-1, IndexEnum::BETWEEN, 4},
+                            {-5, IndexEnum::BETWEEN, 0}, {5, IndexEnum::BETWEEN, -1}, {-6, IndexEnum::BETWEEN, -1}};
+  for (Row const& r : rows) {
+    if (r.expect < 0) CHECK_THROWS(normalize_index("ACGU", r.index, r.kind));
+    else CHECK(normalize_index("ACGU", r.index, r.kind) == r.expect);
+  }
+  auto span = normalize_range("ACGU", -1, 1, IndexEnum::ITEM);
+  CHECK(span.first == 1 && span.second == 3);
+  CHECK_THROWS(normalize_range("ACGU", 0, 4, IndexEnum::ITEM));
 }
