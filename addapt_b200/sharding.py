@@ -61,3 +61,23 @@ def gather_top_designs(scores, seqs, ids, k, dist=None, device=None):
     all_s, all_i, all_q = all_s[valid], all_i[valid], all_q[valid]
     order = np.lexsort((all_i, -all_s))[:kk]          # best score first, ties by global id: independent of the sharding
     return all_s[order], all_q[order], all_i[order]
+
+
+def pick_best_scores(scores, window_size):
+    """Peak picking over one trajectory's scores, as the reference's offline tools select designs from a TSV trajectory
+    (reference tools/utils.py:36-51): repeatedly take the arg-max, record it, and blank +-window_size steps around it with the
+    minimum score, while the maximum is still >= the 75th percentile of the ORIGINAL scores.  Returns the sorted step indices.
+    (The reference loops forever when every score is equal -- blanking cannot push the maximum below the threshold; here a
+    flat trajectory returns its first step, and a zero-width window still blanks the peak itself.)"""
+    s = np.array(scores, dtype=np.float64)
+    if s.size == 0:
+        return []
+    blocked, threshold = s.min(), np.percentile(s, 75)
+    if blocked >= threshold:
+        return [0]
+    peaks = []
+    while s.max() >= threshold:
+        i = int(s.argmax())
+        peaks.append(i)
+        s[max(i - window_size, 0):max(min(i + window_size, s.size), i + 1)] = blocked      # [i-w, i+w), never empty
+    return sorted(peaks)

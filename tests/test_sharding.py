@@ -69,3 +69,21 @@ def test_single_process_gather_is_local_top_k():
     s, q, i = gather_top_designs(scores, seqs, np.arange(100, 150), 5)
     assert list(i) == [100 + k for k in local_top_k(scores, 5)]
     assert np.array_equal(q, seqs[local_top_k(scores, 5)])
+
+
+def test_pick_best_scores_matches_the_reference_rule():
+    """reference tools/utils.py:36-51 -- peaks >= 75th percentile with an exclusion window"""
+    from addapt_b200.sharding import pick_best_scores
+    scores = [0, 1, 5, 1, 0, 0, 4, 0, 0, 9, 8, 0]
+    # 75th percentile = 4.25; the window is [i-w, i+w): the 8 right after the 9 survives w = 1 but not w = 2
+    assert pick_best_scores(scores, 1) == [2, 9, 10]
+    assert pick_best_scores(scores, 2) == [2, 9]
+    assert pick_best_scores(scores, 0) == [2, 9, 10]         # zero-width window: only the peak itself is blanked
+    assert pick_best_scores([3, 3, 3], 2) == [0]             # flat trajectory (the reference would not terminate)
+    assert pick_best_scores([], 5) == []
+    rng = np.random.Generator(np.random.PCG64(8))
+    s = rng.normal(size=400).cumsum()
+    picks = pick_best_scores(s, 25)
+    thr = np.percentile(s, 75)
+    assert all(s[i] >= thr for i in picks)
+    assert all(b - a >= 25 for a, b in zip(picks, picks[1:])) and len(picks) >= 1
