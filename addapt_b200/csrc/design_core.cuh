@@ -162,78 +162,101 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
   return score;
 }
 
-struct McResult {
-  double final_score, best_score;
-  int32_t best_step;
-  uint32_t outcomes[4];      // REJECT, ACCEPT_WORSENED, ACCEPT_UNCHANGED, ACCEPT_IMPROVED
+// Everything a trajectory carries from one step to the next besides its current / best sequences.  A run may be split
+// into several launches (steps [step0, step1) each): the random stream is keyed by the absolute step, so the split does
+// not change a single decision.
+struct McState {
+  double cur_score, best_score;
+  double T_auto, last_diff;          // auto-scaling thermostat: current temperature, most recent score difference
+  int32_t best_step, ntrain;         // best_step = -1: the start sequence; ntrain: filled part of the training window
+  uint32_t outcomes[4];              // REJECT, ACCEPT_WORSENED, ACCEPT_UNCHANGED, ACCEPT_IMPROVED
 };
 
-// One trajectory.  d.cur must hold the start sequence (upper case).  Collective.  kFast requires ACGU/T-only
-// start sequence and contexts (checked on the host).
+// Steps [step0, step1) of one trajectory.  step0 == 0: d.cur holds the start sequence (upper case) and *st is initialised
+// here; otherwise d.cur / d.best / d.train / *st hold what the previous launch left.  *st lives in shared memory; it is
+// read by every thread at entry and rewritten by thread 0 at exit.  Collective.  kFast requires ACGU/T-only start
+// sequence and contexts (checked on the host).
 template <bool kFast, class E>
-ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTableDev& mv, uint64_t seed, uint64_t traj_id, int n_steps,
-                          int thermo_kind, const double* thermo_args, DesignScratch& d, void* fold_small, double* mats, McResult* res,
+ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTableDev& mv, uint64_t seed, uint64_t traj_id, int step0, int step1,
+                          int thermo_kind, const double* thermo_args, DesignScratch& d, void* fold_small, double* mats, McState* st,
                           double* dstate = nullptr) {
   const int n = sp.n;
-  double cur_s = score_construct<kFast>(ex, sp, d.cur, d, fold_small, mats, nullptr, dstate);
-  double best_s = cur_s;
-  int best_step = -1;
-  uint32_t oc0 = 0, oc1 = 0, oc2 = 0, oc3 = 0;
-  for (int p = ex.tid(); p < n; p += ex.nthreads()) d.best[p] = d.cur[p];
+  double cur_s, best_s, T_auto, last_diff;
+  int best_step, ntrain;
+  uint32_t oc0, oc1, oc2, oc3;
+  if (step0 == 0) {
+    // the start sequence is scored by the loop below as "step -1" (one call site of the fold code keeps the kernel small)
+    cur_s = best_s = 0.;
+    best_step = -1;
+    oc0 = oc1 = oc2 = oc3 = 0;
+    ntrain = 0;
+    T_auto = thermo_kind == 2 ? thermo_args[2] : 0.;
+    last_diff = 0.;
+  } else {
+    cur_s = st->cur_score; best_s = st->best_score; best_step = st->best_step;
+    oc0 = st->outcomes[0]; oc1 = st->outcomes[1]; oc2 = st->outcomes[2]; oc3 = st->outcomes[3];
+    ntrain = st->ntrain; T_auto = st->T_auto; last_diff = st->last_diff;
+  }
   ex.sync();
   // auto-scaling thermostat (kind 2, reference src/sampling.cc:371-401): args = {target acceptance rate, training period,
   // initial temperature}.  Every step appends the most recent score difference (0 before the first scored proposal) to the
   // training set; when it holds `period` values, T = max(median / ln(rate), 0) -- "median" being what nth_element leaves at
   // position size/2 -- and the set is cleared.
   const int period = thermo_kind == 2 ? (int)thermo_args[1] : 0;
-  int ntrain = 0;
-  double T_auto = thermo_kind == 2 ? thermo_args[2] : 0., last_diff = 0.;
-  for (int step = 0; step < n_steps && mv.n_free > 0; step++) {
-    double T = thermostat_T(thermo_kind, thermo_args, step);
-    if (thermo_kind == 2) {
-      if (ex.tid() == 0) d.train[ntrain] = last_diff;
-      ntrain++;
-      if (ntrain >= period) {
-        ex.sync();
-        const int mid = ntrain / 2;
-        for (int a = ex.tid(); a < ntrain; a += ex.nthreads()) {      // rank counting: exactly one element has rank mid
-          const double va = d.train[a];
-          int rank = 0;
-          for (int b = 0; b < ntrain; b++) {
-            const double vb = d.train[b];
-            rank += (vb < va) || (vb == va && b < a);
+  for (int step = step0 == 0 ? -1 : step0; step < step1 && (step < 0 || mv.n_free > 0); step++) {
+    const bool start = step < 0;          // score the start sequence: proposal = current, always "accepted", not counted
+    double T = 0., u = 0.;
+    if (start) {
+      for (int p = ex.tid(); p < n; p += ex.nthreads()) { d.prop[p] = d.cur[p]; d.best[p] = d.cur[p]; }
+      ex.sync();
+    } else {
+      T = thermostat_T(thermo_kind, thermo_args, step);
+      if (thermo_kind == 2) {
+        if (ex.tid() == 0) d.train[ntrain] = last_diff;
+        ntrain++;
+        if (ntrain >= period) {
+          ex.sync();
+          const int mid = ntrain / 2;
+          for (int a = ex.tid(); a < ntrain; a += ex.nthreads()) {      // rank counting: exactly one element has rank mid
+            const double va = d.train[a];
+            int rank = 0;
+            for (int b = 0; b < ntrain; b++) {
+              const double vb = d.train[b];
+              rank += (vb < va) || (vb == va && b < a);
+            }
+            if (rank == mid) d.bcast[0] = va;
           }
-          if (rank == mid) d.bcast[0] = va;
+          ex.sync();
+          const double t = d.bcast[0] / log(thermo_args[0]);
+          T_auto = t > 0. ? t : 0.;
+          ntrain = 0;
+          ex.sync();
         }
-        ex.sync();
-        const double t = d.bcast[0] / log(thermo_args[0]);
-        T_auto = t > 0. ? t : 0.;
-        ntrain = 0;
-        ex.sync();
+        T = T_auto;
       }
-      T = T_auto;
+      uint32_t r[4];
+      philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, 0u, (uint32_t)traj_id, (uint32_t)(traj_id >> 32), r);
+      const int slot = (int)(((uint64_t)r[0] * (uint64_t)mv.n_free) >> 32);
+      const uint8_t nt = (uint8_t)("ACGU"[r[1] >> 30]);
+      u = ((double)(r[2] >> 5) * 67108864. + (double)(r[3] >> 6)) / 9007199254740992.;
+      // proposal = current with the closure of the drawn position rewritten
+      for (int p = ex.tid(); p < n; p += ex.nthreads()) d.prop[p] = d.cur[p];
+      ex.sync();
+      bool changed = false;
+      const int clen = mv.closure_len[slot];
+      const uint8_t ntc = complement_nt(nt);
+      for (int q = 0; q < clen; q++) {
+        const int pos = mv.closure_pos[slot][q];
+        const uint8_t want = mv.closure_comp[slot][q] ? ntc : nt;
+        if (d.cur[pos] != want) changed = true;
+      }
+      if (ex.tid() == 0)
+        for (int q = 0; q < clen; q++) d.prop[mv.closure_pos[slot][q]] = mv.closure_comp[slot][q] ? ntc : nt;
+      ex.sync();
+      if (!changed) { oc2++; continue; }                                       // ACCEPT_UNCHANGED: not scored
     }
-    uint32_t r[4];
-    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, 0u, (uint32_t)traj_id, (uint32_t)(traj_id >> 32), r);
-    const int slot = (int)(((uint64_t)r[0] * (uint64_t)mv.n_free) >> 32);
-    const uint8_t nt = (uint8_t)("ACGU"[r[1] >> 30]);
-    const double u = ((double)(r[2] >> 5) * 67108864. + (double)(r[3] >> 6)) / 9007199254740992.;
-    // proposal = current with the closure of the drawn position rewritten
-    for (int p = ex.tid(); p < n; p += ex.nthreads()) d.prop[p] = d.cur[p];
-    ex.sync();
-    bool changed = false;
-    const int clen = mv.closure_len[slot];
-    const uint8_t ntc = complement_nt(nt);
-    for (int q = 0; q < clen; q++) {
-      const int pos = mv.closure_pos[slot][q];
-      const uint8_t want = mv.closure_comp[slot][q] ? ntc : nt;
-      if (d.cur[pos] != want) changed = true;
-    }
-    if (ex.tid() == 0)
-      for (int q = 0; q < clen; q++) d.prop[mv.closure_pos[slot][q]] = mv.closure_comp[slot][q] ? ntc : nt;
-    ex.sync();
-    if (!changed) { oc2++; continue; }                                         // ACCEPT_UNCHANGED: not scored
     const double prop_s = score_construct<kFast>(ex, sp, d.prop, d, fold_small, mats, nullptr, dstate);
+    if (start) { cur_s = best_s = prop_s; continue; }
     const double diff = prop_s - cur_s;
     last_diff = diff;
     const double crit = exp(diff / T);
@@ -248,10 +271,13 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
     }
     ex.sync();
   }
+  ex.sync();
   if (ex.tid() == 0) {
-    res->final_score = cur_s; res->best_score = best_s; res->best_step = best_step;
-    res->outcomes[0] = oc0; res->outcomes[1] = oc1; res->outcomes[2] = oc2; res->outcomes[3] = oc3;
+    st->cur_score = cur_s; st->best_score = best_s; st->best_step = best_step;
+    st->outcomes[0] = oc0; st->outcomes[1] = oc1; st->outcomes[2] = oc2; st->outcomes[3] = oc3;
+    st->ntrain = ntrain; st->T_auto = T_auto; st->last_diff = last_diff;
   }
+  ex.sync();
 }
 
 }  // namespace adp

@@ -59,23 +59,38 @@ template <bool kFast, int G, bool kSmemMats>
 __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
   CtaExec<G> ex;
   DesignSmem s = carve_design_smem<kFast, kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
-  __shared__ McResult res;
+  __shared__ McState st;
   const int n = a.sp.n;
   for (int t = blockIdx.x; t < a.n_traj; t += gridDim.x) {
-    for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.init_seq[p];
+    if (a.step0 == 0) {
+      for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.init_seq[p];
+    } else {
+      // resume: sequences, scalar state and (auto-scaling thermostat) the partly filled training window
+      for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        s.d.cur[p] = a.final_seq[(size_t)t * n + p];
+        s.d.best[p] = a.best_seq[(size_t)t * n + p];
+      }
+      if (threadIdx.x == 0) st = a.state[t];
+      if (a.train_state)
+        for (int q = threadIdx.x; q < a.state[t].ntrain; q += blockDim.x) s.d.train[q] = a.train_state[(size_t)t * a.train_stride + q];
+    }
     __syncthreads();
-    mc_trajectory<kFast>(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.n_steps, a.thermo_kind, a.thermo_args, s.d, s.fold_small, s.mats, &res, s.dstate);
+    mc_trajectory<kFast>(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.step0, a.step1, a.thermo_kind, a.thermo_args, s.d, s.fold_small,
+                         s.mats, &st, s.dstate);
     __syncthreads();
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
-      if (a.final_seq) a.final_seq[(size_t)t * n + p] = s.d.cur[p];
-      if (a.best_seq) a.best_seq[(size_t)t * n + p] = s.d.best[p];
+      a.final_seq[(size_t)t * n + p] = s.d.cur[p];
+      a.best_seq[(size_t)t * n + p] = s.d.best[p];
     }
+    if (a.train_state)
+      for (int q = threadIdx.x; q < st.ntrain; q += blockDim.x) a.train_state[(size_t)t * a.train_stride + q] = s.d.train[q];
     if (threadIdx.x == 0) {
-      if (a.final_score) a.final_score[t] = res.final_score;
-      if (a.best_score) a.best_score[t] = res.best_score;
-      if (a.best_step) a.best_step[t] = res.best_step;
+      a.state[t] = st;
+      if (a.final_score) a.final_score[t] = st.cur_score;
+      if (a.best_score) a.best_score[t] = st.best_score;
+      if (a.best_step) a.best_step[t] = st.best_step;
       if (a.outcomes)
-        for (int k = 0; k < 4; k++) a.outcomes[(size_t)t * 4 + k] = res.outcomes[k];
+        for (int k = 0; k < 4; k++) a.outcomes[(size_t)t * 4 + k] = st.outcomes[k];
     }
     __syncthreads();
   }

@@ -23,12 +23,15 @@ struct McArgs {
   const uint8_t* init_seq;   // sp.n bytes
   int n_traj;
   uint64_t seed, traj_id0;
-  int n_steps;
+  int step0, step1;          // this launch runs steps [step0, step1) of every trajectory (step0 > 0: resumes from `state`)
   int thermo_kind;
   double thermo_args[3];
-  uint8_t* final_seq;        // each output may be NULL
-  double* final_score;
-  uint8_t* best_seq;
+  McState* state;            // [n_traj] carried between launches (never NULL)
+  double* train_state;       // [n_traj * train_stride] training windows of the auto-scaling thermostat, or NULL
+  int train_stride;
+  uint8_t* final_seq;        // current sequences (never NULL: they are part of the carried state)
+  double* final_score;       // the remaining outputs may be NULL
+  uint8_t* best_seq;         // best sequences (never NULL)
   double* best_score;
   int32_t* best_step;
   uint32_t* outcomes;

@@ -59,7 +59,7 @@ struct adp_engine {
   uint64_t launches = 0;
   // staging / scratch, grown on demand
   DevBuf b_seqs, b_ctxseqs, b_dg, b_bppm, b_qi, b_qj, b_qprobs, b_csts, b_motif, b_gmats, b_e, b_structs;
-  DevBuf b_score, b_terms, b_prob, b_mc[8], b_probe, b_redo, b_gmats2;
+  DevBuf b_score, b_terms, b_prob, b_mc[8], b_mcs[4], b_probe, b_redo, b_gmats2;
   bool force_general = false;   // tests: route everything through the general kernels
   MotifDev h_motif{};           // last staged motif record (host copy) and its key
   std::string motif_seq, motif_fold;
@@ -228,6 +228,7 @@ void adp_engine_destroy(adp_engine* e) {
                     &e->b_gmats, &e->b_e, &e->b_structs, &e->b_score, &e->b_terms, &e->b_prob, &e->b_probe, &e->b_redo, &e->b_gmats2};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : e->b_mc) b.release();
+  for (auto& b : e->b_mcs) b.release();
   if (e->d_pf) cudaFree(e->d_pf);
   if (e->d_int) cudaFree(e->d_int);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);

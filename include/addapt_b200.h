@@ -120,7 +120,8 @@ int adp_score_batch(adp_engine *, const adp_problem *, int B, const uint8_t *seq
  * UnbiasedMutationMove (:287-303) and mutate_recursively (:205-282) proposals, Metropolis acceptance
  * (:76-89) and a Fixed (kind 0: {T}), Annealing (kind 1: {T_high, T_low, cycle_len}, :331-338) or AutoScaling
  * (kind 2: {target acceptance rate in (0,1), training period <= 512, initial T}, :371-401) thermostat, all on the device.  Trajectory t draws from Philox4x32-10 keyed by `seed` with counter (step, 0, id_lo, id_hi),
- * id = traj_id0 + t, so results do not depend on how trajectories are sharded over GPUs.
+ * id = traj_id0 + t, so results do not depend on how trajectories are sharded over GPUs -- nor on how the engine splits a
+ * long run into kernel launches (1,024 steps each; the state is carried in device memory).
  * Outputs (each may be NULL; host or device): final_seq/best_seq n_traj*n bytes (upper case ACGU, fixed
  * positions as given), final_score/best_score n_traj doubles, best_step n_traj int32 (-1 = initial),
  * outcomes n_traj*4 uint32 in the order REJECT, ACCEPT_WORSENED, ACCEPT_UNCHANGED, ACCEPT_IMPROVED. */

@@ -187,13 +187,19 @@ int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, 
     carve_design(cv, d, nm);
     SerialExec ex;
     std::memcpy(d.cur, pr->init_seq, pr->n);
-    McResult res;
+    McState res;
     double ta[3] = {targs[0], kind >= 1 ? targs[1] : 0., kind >= 1 ? targs[2] : 1.};
-    if (fast) mc_trajectory<true>(ex, cp.sp, mv[0], seed, traj_id, n_steps, kind, ta, d, small.data(), mats.data(), &res, dstate.data());
-    else mc_trajectory<false>(ex, cp.sp, mv[0], seed, traj_id, n_steps, kind, ta, d, small.data(), mats.data(), &res);
+    // two launches' worth of steps through the carried state, like a chunked adp_mc_run
+    const int cut = n_steps / 2;
+    for (int part = 0; part < 2; part++) {
+      const int s0 = part ? cut : 0, s1 = part ? n_steps : cut;
+      if (part && cut == 0) break;
+      if (fast) mc_trajectory<true>(ex, cp.sp, mv[0], seed, traj_id, s0, part || cut ? s1 : n_steps, kind, ta, d, small.data(), mats.data(), &res, dstate.data());
+      else mc_trajectory<false>(ex, cp.sp, mv[0], seed, traj_id, s0, part || cut ? s1 : n_steps, kind, ta, d, small.data(), mats.data(), &res);
+    }
     std::memcpy(final_seq, d.cur, pr->n);
     std::memcpy(best_seq, d.best, pr->n);
-    *final_score = res.final_score; *best_score = res.best_score; *best_step = res.best_step;
+    *final_score = res.cur_score; *best_score = res.best_score; *best_step = res.best_step;
     for (int k = 0; k < 4; k++) outcomes[k] = res.outcomes[k];
     return 0;
   } catch (std::string& er) { g_err = er; return -1; }

@@ -235,6 +235,19 @@ def test_monte_carlo_matches_oracle_step_for_step(oracle, engine):
             assert list(r["outcomes"][t]) == a["outcomes"] and r["best_step"][t] == a["best_step"]
             assert r["final_score"][t] == pytest.approx(a["final_score"], rel=SC_RTOL)
             assert r["best_score"][t] == pytest.approx(a["best_score"], rel=SC_RTOL)
+    # long runs are split into launches that carry the state in device memory: the split must not change anything
+    import os
+    for thermo in (("annealing", 5.0, 0.0, 300), ("auto", 0.5, 8, 1.0)):
+        whole = engine.mc_run(pr, 5, 77, 45, thermostat=thermo)
+        os.environ["ADDAPT_B200_MC_CHUNK"] = "7"
+        try:
+            parts = engine.mc_run(pr, 5, 77, 45, thermostat=thermo)
+        finally:
+            del os.environ["ADDAPT_B200_MC_CHUNK"]
+        assert whole["final_seq"] == parts["final_seq"] and whole["best_seq"] == parts["best_seq"]
+        assert np.array_equal(whole["outcomes"], parts["outcomes"]) and np.array_equal(whole["best_step"], parts["best_step"])
+        assert np.array_equal(whole["final_score"], parts["final_score"]) and np.array_equal(whole["best_score"], parts["best_score"])
+    assert engine.mc_run(pr, 2, 3, 0)["best_step"].tolist() == [-1, -1]          # zero steps: the start sequence, scored
     # sharding invariance: trajectory ids, not launch geometry, define the streams
     whole = engine.mc_run(pr, 4, 5, 25, traj_id0=0)
     parts = [engine.mc_run(pr, 2, 5, 25, traj_id0=0), engine.mc_run(pr, 2, 5, 25, traj_id0=2)]
