@@ -23,14 +23,32 @@ def local_top_k(scores, k):
     return order[:k]
 
 
-def gather_top_designs(scores, seqs, ids, k, dist=None, device=None):
+def _first_of_each_sequence(order, seqs, k):
+    """walk `order` (best first) and keep the first occurrence of every distinct sequence, up to k"""
+    seen, keep = set(), []
+    for idx in order:
+        key = seqs[idx].tobytes()
+        if key not in seen:
+            seen.add(key)
+            keep.append(idx)
+            if len(keep) == k:
+                break
+    return np.asarray(keep, dtype=np.int64)
+
+
+def gather_top_designs(scores, seqs, ids, k, dist=None, device=None, distinct=False):
     """Every rank passes its local trajectories' best scores [m], best sequences [m, n] (uint8) and global ids [m];
-    every rank gets the global top-k (scores [k], seqs [k, n], ids [k]), best first, identical on all ranks.
+    every rank gets the global top-k (scores [<=k], seqs [<=k, n], ids [<=k]), best first, identical on all ranks.
+    distinct=True ranks DESIGNS rather than trajectories: of the trajectories that ended on the same sequence only the one
+    with the lowest id is kept (many trajectories converge to the same optimum).
     `dist` = torch.distributed (initialised) or None for a single process."""
     scores = np.asarray(scores, dtype=np.float64)
     seqs = np.asarray(seqs, dtype=np.uint8)
     ids = np.asarray(ids, dtype=np.int64)
-    pick = local_top_k(scores, k)
+    if distinct:
+        pick = _first_of_each_sequence(np.lexsort((ids, -scores)), seqs, k)
+    else:
+        pick = local_top_k(scores, k)
     loc_s, loc_q, loc_i = scores[pick], seqs[pick], ids[pick]
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return loc_s, loc_q, loc_i
@@ -59,7 +77,8 @@ def gather_top_designs(scores, seqs, ids, k, dist=None, device=None):
     all_q = torch.cat(Q).cpu().numpy()
     valid = all_i >= 0
     all_s, all_i, all_q = all_s[valid], all_i[valid], all_q[valid]
-    order = np.lexsort((all_i, -all_s))[:kk]          # best score first, ties by global id: independent of the sharding
+    order = np.lexsort((all_i, -all_s))               # best score first, ties by global id: independent of the sharding
+    order = _first_of_each_sequence(order, all_q, kk) if distinct else order[:kk]
     return all_s[order], all_q[order], all_i[order]
 
 

@@ -43,6 +43,16 @@ s, q, i = gather_top_designs(scores[lo:hi], seqs[lo:hi], np.arange(lo, hi), K, d
 order = np.lexsort((np.arange(N), -scores))[:K]
 assert np.array_equal(i, order), (rank, i, order)
 assert np.array_equal(s, scores[order]) and np.array_equal(q, seqs[order])
+# distinct designs: many trajectories end on the same sequence; the merged list holds each sequence once (lowest id wins)
+dup = seqs[rng.integers(0, 40, N)]
+s2, q2, i2 = gather_top_designs(scores[lo:hi], dup[lo:hi], np.arange(lo, hi), K, dist, distinct=True)
+want, seen = [], set()
+for idx in np.lexsort((np.arange(N), -scores)):
+    if dup[idx].tobytes() not in seen:
+        seen.add(dup[idx].tobytes()); want.append(idx)
+    if len(want) == K: break
+assert np.array_equal(i2, np.array(want)), (rank, i2, want)
+assert len({q.tobytes() for q in q2}) == len(q2)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")

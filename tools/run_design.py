@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--topk", type=int, default=1024)
     ap.add_argument("--seed", type=int, default=2016)
     ap.add_argument("--thermostat", default="5 to 0 in 300 steps")
+    ap.add_argument("--distinct", action="store_true", help="rank distinct designs instead of trajectories")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -57,7 +58,7 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     seqs = np.frombuffer("".join(r["best_seq"]).encode(), dtype=np.uint8).reshape(b - a, -1)
     tg = time.perf_counter()
-    top_s, top_q, top_i = gather_top_designs(r["best_score"], seqs, np.arange(a, b), args.topk, dist if world > 1 else None, torch.device("cuda", local))
+    top_s, top_q, top_i = gather_top_designs(r["best_score"], seqs, np.arange(a, b), args.topk, dist if world > 1 else None, torch.device("cuda", local), distinct=args.distinct)
     tg = time.perf_counter() - tg
     if rank == 0:
         top_seqs = [bytes(q).decode() for q in top_q]
