@@ -102,6 +102,10 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   w.cp = cv.take<uint8_t>(w.ld);
   w.cells = cv.take<uint16_t>(w.ld);
   w.counter = cv.take<int>(4);
+  w.hpw = cv.take<double>(w.ld);
+  w.spx = cv.take<int16_t>((size_t)3 * w.ld);
+  w.lvoff = cv.take<int>(32);
+  w.qctr = cv.take<int>(2);
   w.qb = mats;
   w.qm = qm_ext ? qm_ext : mats + t4_count(n) + 1;
   w.scaleG = job.T->scale;
@@ -114,6 +118,7 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   for (int k = ex.tid(); k < w.ld; k += ex.nthreads()) w.vecp(10)[k] = job.T->eMLb[k];
   load_context(ex, c, job.seq, job.cst, job.motif);   // ends with a barrier
   if (!fast_codes(ex, c, w)) w.counter[2] = 1;
+  fast_special_hairpins(ex, c, job.T, w);
   ex.sync();
   if (w.counter[2]) return false;
 

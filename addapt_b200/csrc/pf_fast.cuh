@@ -32,7 +32,33 @@
 #pragma once
 #include "fold_common.cuh"
 
+#if defined(__CUDA_ARCH__)
+#define ADP_UNROLL _Pragma("unroll")
+#define ADP_NOUNROLL _Pragma("unroll 1")
+#else
+#define ADP_UNROLL
+#define ADP_NOUNROLL
+#endif
+
 namespace adp {
+
+// Phase timing for tuning (build with -DADP_PHASE_PROFILE; tools/phase_profile.sh): every warp of CTA 0 accumulates clock64()
+// deltas per phase of the column loop and prints them for the first jobs.  Off in the product build.
+#if defined(ADP_PHASE_PROFILE) && defined(__CUDACC__)
+static __device__ int g_prof_reports;
+#endif
+#if defined(ADP_PHASE_PROFILE) && defined(__CUDA_ARCH__)
+#define ADP_PROF_DECL long long prof_[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev_ = clock64();
+#define ADP_TICK(s_) { const long long t_ = clock64(); prof_[s_] += t_ - tprev_; tprev_ = t_; }
+#define ADP_PROF_REPORT(tag_)                                                                                                   \
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && atomicAdd(&g_prof_reports, 1) < 48)                                          \
+    printf(tag_ " warp %d: cells %lld drain1 %lld wait1 %lld vec %lld levels %lld rows %lld drain2 %lld wait2 %lld | head %lld corners %lld axis %lld ml %lld reduce %lld store %lld\n", (int)(threadIdx.x >> 5), \
+           prof_[0], prof_[1], prof_[2], prof_[3], prof_[4], prof_[5], prof_[6], prof_[7], prof_[8], prof_[9], prof_[10], prof_[11], prof_[12], prof_[13]);
+#else
+#define ADP_PROF_DECL
+#define ADP_TICK(s_)
+#define ADP_PROF_REPORT(tag_)
+#endif
 
 constexpr int kFastLevels = 14;       // level sums per thread: s = 4+par, 6+par, ..., 30+par
 constexpr int kFastMaxN = 320;        // longest construct the fast path takes (ADP_MAX_LEN)
@@ -45,18 +71,26 @@ struct PfHot {                        // shared memory, staged once per CTA
   double tapB[32];                    // bulge[u] * scale[u+2]                      (u >= 2)
   double tap1n[32];                   // interior[u+1] * ninio[u-1] * scale[u+3]    (1 x u loop, u >= 3)
   double scale1, scale2, eMLb1, MLclosing, TermAU, pad;
+  // what hairpins, stems at the sequence ends, exterior stems and the corner candidates read: staged so that no L2-latency
+  // load sits on the path of a cell (only int11 / int21 / int22 and the special-hairpin weights stay in global memory)
+  double stack[64];                   // [type][type2]
+  double mm23[200], mmH[200], mmExt[200];     // [type][5' side neighbour][3' side neighbour]
+  double dangle5[40], dangle3[40];
+  double cfac[16];                    // per corner candidate q: scale[u1+u2+2] * (bulge[1] | interior[5] * ninio[1] | 1)
+  double one, MLintern;
 };
 
 // size-indexed factors of the generic interior loops; read with compile-time indices
 struct FastConst {
-  double ip[32];                      // interior[s] * scale[s+2]
-  double nin[32];                     // ninio factor of asymmetry d
+  double ip[32];                      // [parity][q]: interior[s] * scale[s+2] of level s = 4 + parity + 2q (0 beyond kMaxLoop)
+  double nin[32];                     // [parity][q]: ninio factor of asymmetry s - 4
 };
 
 ADP_HD void fill_fast_const(FastConst* fc, const PfTables* T) {
-  for (int q = 0; q < 32; q++) {
-    fc->ip[q] = q <= 30 ? T->interior[q] * T->scale[q + 2] : 0.;
-    fc->nin[q] = q <= 30 ? T->ninio[q] : 0.;
+  for (int t = 0; t < 32; t++) {
+    const int s = 4 + (t >> 4) + 2 * (t & 15);
+    fc->ip[t] = s <= kMaxLoop ? T->interior[s] * T->scale[s + 2] : 0.;
+    fc->nin[t] = s <= kMaxLoop ? T->ninio[s - 4] : 0.;
   }
 }
 
@@ -69,6 +103,13 @@ static FastConst h_fast_const;                    // host emulation
 #else
 #define ADP_FC h_fast_const
 #endif
+
+// the 9 interior-loop candidates that go through the full tables: (u1,u2) =
+// (0,0)(0,1) (1,0)(1,1)(1,2) (2,1)(2,2)(2,3) (3,2), packed 4 bits each
+ADP_HD void corner_u(int q, int* u1, int* u2) {
+  *u1 = (int)((0x322211100ull >> (4 * q)) & 15);
+  *u2 = (int)((0x232121010ull >> (4 * q)) & 15);
+}
 
 template <class E>
 ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
@@ -89,9 +130,25 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
     H->tapB[q] = (q >= 2 && q <= 30) ? T->bulge[q] * T->scale[q + 2] : 0.;
     H->tap1n[q] = (q >= 3 && q <= 29) ? T->interior[q + 1] * T->ninio[q - 1] * T->scale[q + 3] : 0.;
   }
+  for (int q = ex.tid(); q < 200; q += ex.nthreads()) {
+    H->mm23[q] = (&T->mm23I[0][0][0])[q];
+    H->mmH[q] = (&T->mmH[0][0][0])[q];
+    H->mmExt[q] = (&T->mmExt[0][0][0])[q];
+    if (q < 64) H->stack[q] = (&T->stack[0][0])[q];
+    if (q < 40) { H->dangle5[q] = (&T->dangle5[0][0])[q]; H->dangle3[q] = (&T->dangle3[0][0])[q]; }
+    if (q < 16) {
+      int u1 = 0, u2 = 0;
+      if (q < 9) corner_u(q, &u1, &u2);
+      double f = q < 9 ? T->scale[u1 + u2 + 2] : 0.;
+      if (q == 1 || q == 2) f *= T->bulge[1];
+      if (q == 7 || q == 8) f *= T->interior[5] * T->ninio[1];
+      H->cfac[q] = f;
+    }
+  }
   if (ex.tid() == 0) {
     H->scale1 = T->scale[1]; H->scale2 = T->scale[2]; H->eMLb1 = T->eMLb[1];
     H->MLclosing = T->MLclosing; H->TermAU = T->TermAU; H->pad = 0.;
+    H->one = 1.; H->MLintern = T->MLintern;
   }
 #if !defined(__CUDA_ARCH__)
   fill_fast_const(&h_fast_const, T);
@@ -110,6 +167,10 @@ struct FastWork {
   uint8_t* cp;     // [ld] code of (S[p], S[p-1])
   uint16_t* cells; // [ld] rows of the current column that can pair
   int* counter;    // [4]: 0/1 list lengths by column parity, 2 "declined" flag
+  double* hpw;     // [ld]: hairpin[u] * scale[u+2] by loop size u
+  int16_t* spx;    // [3][ld]: index of the special hairpin (tri / tetra / hexa loop) closed at i, or -1
+  int* lvoff;      // [32]: byte offsets of the row candidates of the level recursion, [parity][level], for the column being prepared
+  int* qctr;       // [2]: chunk counters of the deferred work queue, by column parity
   double* dstate;  // NULL: every thread keeps the level sums of its anti-diagonal in registers (needs 2*R <= threads);
                    // else [2*R*kFastLevels] doubles of memory holding them (host emulation; constructs longer than threads/2)
   int ld;          // vector length (>= n + 4)
@@ -126,7 +187,7 @@ ADP_HD size_t fast_state_doubles(int n) { return (size_t)2 * fast_R(n) * kFastLe
 
 ADP_HD size_t fast_small_bytes(int n) {
   const size_t ld = (size_t)fast_ld(n);
-  return sizeof(PfHot) + 64 + ctx_bytes(n) + kFastVectors * ld * sizeof(double) + 2 * ld + 2 * ld + 64 + 16 * 12;
+  return sizeof(PfHot) + 64 + ctx_bytes(n) + kFastVectors * ld * sizeof(double) + 2 * ld + 2 * ld + 64 + 16 * 12 + 34 * sizeof(int) + 32 + ld * sizeof(double) + 3 * ld * sizeof(int16_t) + 32;
 }
 ADP_HD size_t fast_matrix_doubles(int n) { return 2 * t4_count(n) + 2; }
 
@@ -149,29 +210,78 @@ ADP_HD int group_lg(int m, int nt_lg, int cap_lg) {
   return lg < 0 ? 0 : lg;
 }
 
-// multiloop / exterior stem factor of the pair (i,j) seen from outside (neighbours i-1, j+1 dangle when they exist)
-ADP_HD double fast_stem_ml(const SeqCtx& c, const PfHot& H, const PfTables* G, const FastWork& w, int type, int i, int j) {
+// multiloop / exterior stem factor of the pair (i,j) seen from outside (neighbours i-1, j+1 dangle when they exist); same
+// products in the same order as stem_x (fold_common.cuh)
+ADP_HD double fast_stem_ml(const SeqCtx& c, const PfHot& H, const FastWork& w, int type, int i, int j) {
   if (i > 1 && j < c.n) return H.FM[(w.cn[j] << 4) | w.cp[i]];
-  return stem_x(*G, type, i > 1, c.S[i - 1], j < c.n, c.S[j + 1], false);
+  double e = 1.;
+  if (i > 1) e = H.dangle5[type * 5 + c.S[i - 1]];
+  else if (j < c.n) e = H.dangle3[type * 5 + c.S[j + 1]];
+  if (type > 2) e *= H.TermAU;
+  return e * H.MLintern;
 }
-ADP_HD double fast_stem_ext(const SeqCtx& c, const PfTables* G, int type, int i, int j) {
-  return stem_x(*G, type, i > 1, c.S[i - 1], j < c.n, c.S[j + 1], true);
+ADP_HD double fast_stem_ext(const SeqCtx& c, const PfHot& H, int type, int i, int j) {
+  double e = 1.;
+  if (i > 1 && j < c.n) e = H.mmExt[(type * 5 + c.S[i - 1]) * 5 + c.S[j + 1]];
+  else if (i > 1) e = H.dangle5[type * 5 + c.S[i - 1]];
+  else if (j < c.n) e = H.dangle3[type * 5 + c.S[j + 1]];
+  if (type > 2) e *= H.TermAU;
+  return e;
+}
+
+// special hairpins of the job: index into the tri / tetra / hexa loop tables per 5' end, found once per job
+template <class E>
+ADP_HD void fast_special_hairpins(const E& ex, const SeqCtx& c, const PfTables* G, FastWork& w) {
+  const int n = c.n, ld = w.ld;
+  for (int t = ex.tid(); t < 3 * ld; t += ex.nthreads()) {
+    const int cls = t / ld, i = t - cls * ld;
+    const int u = cls == 0 ? 3 : cls == 1 ? 4 : 6;
+    int idx = -1;
+    uint32_t code;
+    if (i >= 1 && i + u + 1 <= n && pack_window(c.S, i, u + 2, &code)) {
+      const uint32_t* codes = u == 4 ? G->tetra_code : u == 6 ? G->hex_code : G->tri_code;
+      const int cnt = u == 4 ? G->n_tetra : u == 6 ? G->n_hex : G->n_tri;
+      for (int k = 0; k < cnt; k++)
+        if (codes[k] == code) { idx = k; break; }
+    }
+    w.spx[t] = (int16_t)idx;
+  }
+  for (int u = ex.tid(); u < ld; u += ex.nthreads()) w.hpw[u] = G->hairpin[u] * G->scale[u + 2];
 }
 
 template <bool kCst>
-ADP_HD double fast_hairpin(const SeqCtx& c, const PfTables* G, const FastWork& w, double motif_boltz, int i, int j, int type) {
+ADP_HD double fast_hairpin(const SeqCtx& c, const PfHot& H, const PfTables* G, const FastWork& w, double motif_boltz, int i, int j, int type) {
   const int u = j - i - 1;
   if (kCst && (int)c.upr[i + 1] < u) return 0.;
-  double q = hairpin_x(*G, G, c.S, i, j, type) * w.scaleG[u + 2];
+  int sx = -1;
+  if (u == 3) sx = w.spx[i];
+  else if (u == 4) sx = w.spx[w.ld + i];
+  else if (u == 6) sx = w.spx[2 * w.ld + i];
+  double q;
+  if (sx >= 0) q = (u == 4 ? G->tetra_x : u == 6 ? G->hex_x : G->tri_x)[sx] * w.scaleG[u + 2];
+  else if (u == 3) q = type > 2 ? w.hpw[3] * H.TermAU : w.hpw[3];
+  else q = w.hpw[u] * H.mmH[(type * 5 + c.S[i + 1]) * 5 + c.S[j - 1]];
   if (is_motif_site(c, i, j)) q *= motif_boltz;   // the bound motif REPLACES the empty loop
   return q;
 }
 
-// the 9 interior-loop candidates that go through the full tables: (u1,u2) =
-// (0,0)(0,1) (1,0)(1,1)(1,2) (2,1)(2,2)(2,3) (3,2), packed 4 bits each
-ADP_HD void corner_u(int q, int* u1, int* u2) {
-  *u1 = (int)((0x322211100ull >> (4 * q)) & 15);
-  *u2 = (int)((0x232121010ull >> (4 * q)) & 15);
+// Corner candidate q of the closing pair (type; neighbours si1, sj1 inside) with the inner pair (type2 already reversed;
+// neighbours sp1 = S[k-1], sq1 = S[l+1]): the weight is  *fac * (*returned address)  -- same cases as interior_x
+// (fold_common.cuh), split so that the one load that may go to global memory (int11 / int21 / int22) can be issued early.
+ADP_HD const double* corner_entry(const PfHot& H, const PfTables* G, int q, int type, int type2, int si1, int sj1, int sp1, int sq1, double* fac) {
+  double f = H.cfac[q];
+  const double* p;
+  if (q <= 2) p = &H.stack[type * 8 + type2];
+  else if (q == 3) p = &G->int11[type][type2][si1][sj1];
+  else if (q == 4) p = &G->int21[type][type2][si1][sq1][sj1];
+  else if (q == 5) p = &G->int21[type2][type][sq1][si1][sp1];
+  else if (q == 6) p = &G->int22[type][type2][si1][sp1][sq1][sj1];
+  else {
+    f *= H.mm23[(type * 5 + si1) * 5 + sj1] * H.mm23[(type2 * 5 + sq1) * 5 + sp1];
+    p = &H.one;
+  }
+  *fac = f;
+  return p;
 }
 
 template <class E>
@@ -192,30 +302,40 @@ ADP_HD bool fast_codes(const E& ex, const SeqCtx& c, FastWork& w) {
   return ok;     // per thread; the caller combines
 }
 
-// One level of the recursion for the thread that owns an anti-diagonal.  d[Q] holds the sum of level S = 4 + PAR + 2Q.
-// P1 / P2 are the ADDRESSES of the two candidates with u1 = 2 / u2 = 2 and C1 / C2 their hard-constraint gates; a level
-// that is off for this thread (S > smax, or the gate is closed) reads the always-zero word `zp` instead, so the step is
-// branch-free: every lane of the warp runs the same instructions whatever its row.  Everything indexed by S or Q is a
-// compile-time constant, so d[] stays in registers and the size factors are constant-bank operands.
-#define ADP_LEVEL_STEP(PAR, Q, P1, C1, P2, C2)                                         \
-  if (4 + (PAR) + 2 * (Q) <= kMaxLoop) {                                              \
-    constexpr int S = 4 + (PAR) + 2 * (Q);                                            \
-    const bool on = S <= smax;                                                        \
-    const double* p1 = (on && (C1)) ? (P1) : zp;                                      \
-    const double* p2 = (S > 4 && on && (C2)) ? (P2) : zp;                             \
-    double v = ADP_FC.nin[S - 4 > 0 ? S - 4 : 0] * (*p1 + *p2);                       \
-    if ((Q) > 0) v += (on && g) ? d[(Q) > 0 ? (Q) - 1 : 0] : 0.;                      \
-    if (S >= 6) gen += ADP_FC.ip[S] * v;                                              \
+struct alignas(16) Int4 { int x, y, z, w; };
+
+// One level of the recursion for the thread that owns an anti-diagonal.  d[Q] holds the sum of level S = 4 + par + 2Q; the level
+// parity `par` is a run-time (warp-uniform) value, so both parities share one code path: everything that depends on it comes
+// from tables indexed [par][Q] (size factors in the constant bank, row offsets in shared memory) or is folded into the limits
+// (sm1 / sm2 = largest 4 + 2Q that is on for the row / column candidate).  ADDR1 / ADDR2 are the ADDRESSES of the two candidates
+// with u1 = 2 / u2 = 2 and C1 / C2 their hard-constraint gates; a candidate that is off reads the always-zero word `zp` instead, so
+// the step is branch-free: every lane of the warp runs the same instructions whatever its row.  Q is a compile-time constant, so
+// d[] stays in registers.  When unconstrained, the carried sum needs no gate: a level that is off here was off one step earlier
+// on the anti-diagonal too, i.e. it carries zero.
+#define ADP_LEVEL_STEP(Q, ADDR1, C1, ADDR2, C2)                                        \
+  {                                                                                   \
+    const double* p1 = (4 + 2 * (Q) <= sm1 && C1(Q)) ? ADDR1(Q) : zp;                 \
+    const double* p2 = (4 + 2 * (Q) <= sm2 && ((Q) > 0 || par != 0) && C2(Q)) ? ADDR2(Q) : zp; \
+    double v = fcn[Q] * (*p1 + *p2);                                                  \
+    if ((Q) > 0) v += (!kCst || (4 + 2 * (Q) <= sm && g)) ? d[(Q) > 0 ? (Q) - 1 : 0] : 0.;     \
+    if ((Q) > 0) gen += fci[Q] * v;                                                   \
     d[Q] = v;                                                                         \
   }
-#define ADP_LEVEL_PASS(PAR, B1, C1, B2, C2)                                                            \
-  ADP_LEVEL_STEP(PAR, 13, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 12, B1, C1, B2, C2) \
-  ADP_LEVEL_STEP(PAR, 11, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 10, B1, C1, B2, C2) \
-  ADP_LEVEL_STEP(PAR, 9, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 8, B1, C1, B2, C2) \
-  ADP_LEVEL_STEP(PAR, 7, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 6, B1, C1, B2, C2) \
-  ADP_LEVEL_STEP(PAR, 5, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 4, B1, C1, B2, C2) \
-  ADP_LEVEL_STEP(PAR, 3, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 2, B1, C1, B2, C2) \
-  ADP_LEVEL_STEP(PAR, 1, B1, C1, B2, C2) ADP_LEVEL_STEP(PAR, 0, B1, C1, B2, C2)
+#define ADP_LEVEL_PASS(A1, C1, A2, C2)                                                 \
+  ADP_LEVEL_STEP(13, A1, C1, A2, C2) ADP_LEVEL_STEP(12, A1, C1, A2, C2) ADP_LEVEL_STEP(11, A1, C1, A2, C2) \
+  ADP_LEVEL_STEP(10, A1, C1, A2, C2) ADP_LEVEL_STEP(9, A1, C1, A2, C2) ADP_LEVEL_STEP(8, A1, C1, A2, C2)  \
+  ADP_LEVEL_STEP(7, A1, C1, A2, C2) ADP_LEVEL_STEP(6, A1, C1, A2, C2) ADP_LEVEL_STEP(5, A1, C1, A2, C2)  \
+  ADP_LEVEL_STEP(4, A1, C1, A2, C2) ADP_LEVEL_STEP(3, A1, C1, A2, C2) ADP_LEVEL_STEP(2, A1, C1, A2, C2)  \
+  ADP_LEVEL_STEP(1, A1, C1, A2, C2) ADP_LEVEL_STEP(0, A1, C1, A2, C2)
+// the row offsets of one parity: 16 ints, four vector loads
+#define ADP_LEVEL_OFFSETS(LVO)                                                                            \
+  int lo[16];                                                                                             \
+  {                                                                                                       \
+    const Int4* lv4 = reinterpret_cast<const Int4*>(LVO);                                                 \
+    const Int4 o0 = lv4[0], o1 = lv4[1], o2 = lv4[2], o3 = lv4[3];                                        \
+    lo[0] = o0.x; lo[1] = o0.y; lo[2] = o0.z; lo[3] = o0.w; lo[4] = o1.x; lo[5] = o1.y; lo[6] = o1.z; lo[7] = o1.w;       \
+    lo[8] = o2.x; lo[9] = o2.y; lo[10] = o2.z; lo[11] = o2.w; lo[12] = o3.x; lo[13] = o3.y; lo[14] = o3.z; lo[15] = o3.w; \
+  }
 #define ADP_LEVEL_ZERO()                                                                                  \
   d[0] = d[1] = d[2] = d[3] = d[4] = d[5] = d[6] = d[7] = d[8] = d[9] = d[10] = d[11] = d[12] = d[13] = 0.;
 
@@ -255,10 +375,23 @@ ADP_HD double qm_row_terms(const double* qm, const double* qm1, const double* eM
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Deferred work queue.  Work that is not on the column-to-column critical path (Qm of the previous column in the inside pass,
+// the multiloop carrier A of the next column in the outside pass) is cut into warp-sized chunks; a warp that has nothing else
+// to do in either interval of a column takes the next chunk.  One counter per column parity, reset a column ahead.
+template <class E>
+ADP_HD int grab_chunk(const E& ex, int* ctr) {
+  int c = 0;
+  if (ex.lane() == 0) c = ex.atomic_inc(ctr);
+  return ex.warp_bcast(c, 0);
+}
+
+ADP_HD int qm1_slot(int j) { const int r = j % 3; return r == 2 ? 6 : r; }     // Qm1 columns rotate through vectors 0, 1, 6
+
+// ---------------------------------------------------------------------------------------------------
 // inside pass.  Returns Z = Q(1,n) (scaled) on every thread.
-// vector roles: 0/1 Qm1 columns by parity, 2 and 7 exterior terms per row by column parity, 3 xA (Qb * terminal factor, column
-// j-1), 4/5 x1n (Qb * 1xn mismatch, by column parity), 6/7/8 xI (Qb * generic mismatch, by column mod 3), 9 q1,
-// 10 eMLb powers, 11/12 generic-loop sums per level parity.
+// vector roles: 0/1/6 Qm1 columns (by column mod 3), 2 and 7 exterior terms per row by column parity, 3 xA (Qb * terminal
+// factor, column j-1), 4/5 x1n (Qb * 1xn mismatch, by column parity), 8 hairpin weight / 13 multiloop stem factor / 14 exterior
+// stem factor * q1 of the cells of the column being prepared, 9 q1, 10 eMLb powers, 11/12 generic-loop sums per level parity.
 template <bool kCst, class E>
 ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const PfTables* G, double motif_boltz, FastWork& w) {
   const int n = c.n, nt = ex.nthreads(), tid = ex.tid(), ld = w.ld, R = w.R;
@@ -271,19 +404,23 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
   const uint8_t* const cn = w.cn;
   const uint8_t* const cp = w.cp;
   for (int k = tid; k < ntri; k += nt) { qb[k] = 0.; qm[k] = 0.; }
-  for (int k = tid; k < 13 * ld; k += nt)
+  for (int k = tid; k < 15 * ld; k += nt)
     if (k < 10 * ld || k >= 11 * ld) w.vbase[k] = 0.;
   double* const q1 = w.vecp(9);
   const double* const eMLbS = w.vecp(10);
   double* const xA = w.vecp(3);
   double* const gen0 = w.vecp(11);
   double* const gen1 = w.vecp(12);
+  double* const hp = w.vecp(8);
+  double* const smv = w.vecp(13);
+  double* const sev = w.vecp(14);
   double d[kFastLevels];     // level sums of this thread's anti-diagonal (registers)
   const double* const zp = &H.pad;   // an always-zero word for levels that are off
   ADP_LEVEL_ZERO()
+  ADP_PROF_DECL
   if (mem_state)
     for (int k = tid; k < 2 * R * kFastLevels; k += nt) w.dstate[k] = 0.;
-  if (tid == 0) { w.counter[0] = 0; w.counter[1] = 0; }
+  if (tid == 0) { w.counter[0] = 0; w.counter[1] = 0; w.qctr[0] = 0; w.qctr[1] = 0; }
   ex.sync();
   const double s1 = H.scale1, eb1 = H.eMLb1;
   if (tid == 0) {
@@ -293,15 +430,15 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
   }
 
   // everything column `jn` needs before its cells can be evaluated, and that does not depend on column jn-1:
-  // level sums of the generic loops, the unpaired-extension part of Qm1, the list of cells
+  // level sums of the generic loops, the unpaired-extension part of Qm1, the list of cells and their sequence-only factors
   auto prepare_column = [&](int jn) {
     const int nr = jn - 4;
     const bool cuj = !kCst || can_unpair(c, jn);
     const bool cuj1 = !kCst || can_unpair(c, jn - 1);
     const int upl_j1 = kCst ? (int)c.upl[jn - 1] : 1000;
     const double* col3 = qb + (((jn - 7) * (jn - 8)) >> 1) - 2;   // Qb*FI(k, jn-3) = col3[k + 1]
-    const double* qm1_prev = w.vecp((jn - 1) & 1);
-    double* qm1_cur = w.vecp(jn & 1);
+    const double* qm1_prev = w.vecp(qm1_slot(jn - 1));
+    double* qm1_cur = w.vecp(qm1_slot(jn));
     int* counter = w.counter + (jn & 1);
     for (int task = tid; task < 2 * half; task += nt) {
       const int par = task >= half ? 1 : 0;          // warp-uniform: the two parities are separate code paths
@@ -312,23 +449,33 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       if (key < jn + 1) key += R;
       const int i = key - jn;
       if (i >= 1 && i <= nr) {
-        int smax = jn - i - 6;
-        if (smax > kMaxLoop) smax = kMaxLoop;
+        int sm = jn - i - 6;
+        if (sm > kMaxLoop) sm = kMaxLoop;
+        sm -= par;                                     // level Q is on iff 4 + 2Q <= sm
         double gen = 0.;
-        if (smax >= 4) {
+#if defined(ADP_X_NOLEVELS)
+        if (false) {
+#else
+        if (sm + par >= 4) {
+#endif
           const int upr_i1 = kCst ? (int)c.upr[i + 1] : 1000;
           const bool g = upr_i1 >= 1 && cuj1;
           const bool ok1 = upr_i1 >= 2, ok2 = upl_j1 >= 2;
-          const double* xi = col3 + i;                 // xi[S] = Qb*FI(i+S-1, jn-3)
-          const double* qrow = qb + i + 2;             // Qb*FI(i+3, l) = qrow[(l-4)(l-5)/2]
-#define ADP_P1 (qrow + (((jn - 3 - S) * (jn - 4 - S)) >> 1))
-#define ADP_C1 (!kCst || (ok1 && upl_j1 >= S - 2))
-#define ADP_P2 (xi + S)
-#define ADP_C2 (!kCst || (ok2 && upr_i1 >= S - 2))
-          if (par) { ADP_LEVEL_PASS(1, ADP_P1, ADP_C1, ADP_P2, ADP_C2) } else { ADP_LEVEL_PASS(0, ADP_P1, ADP_C1, ADP_P2, ADP_C2) }
-#undef ADP_P1
+          const int sm1 = sm, sm2 = sm;
+          const int lim1 = upl_j1 - par - 2, lim2 = upr_i1 - par - 2;     // constraint gates: S - 2 unpaired bases on the other side
+          const double* xi = col3 + i + par + 4;       // Qb*FI(i+S-1, jn-3) = xi[2Q]
+          const char* qrow = reinterpret_cast<const char*>(qb + i + 2);   // Qb*FI(i+3, l) = qrow[(l-4)(l-5)/2], l = jn+1-S: offset from the table
+          const double* fcn = ADP_FC.nin + (par << 4);
+          const double* fci = ADP_FC.ip + (par << 4);
+          ADP_LEVEL_OFFSETS(w.lvoff + (par << 4))
+#define ADP_A1(Q) reinterpret_cast<const double*>(qrow + lo[Q])
+#define ADP_C1(Q) (!kCst || (ok1 && 2 * (Q) <= lim1))
+#define ADP_A2(Q) (xi + 2 * (Q))
+#define ADP_C2(Q) (!kCst || (ok2 && 2 * (Q) <= lim2))
+          ADP_LEVEL_PASS(ADP_A1, ADP_C1, ADP_A2, ADP_C2)
+#undef ADP_A1
 #undef ADP_C1
-#undef ADP_P2
+#undef ADP_A2
 #undef ADP_C2
         } else {
           ADP_LEVEL_ZERO()
@@ -338,26 +485,79 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       if (mem_state)
         for (int q = 0; q < kFastLevels; q++) w.dstate[(size_t)task * kFastLevels + q] = d[q];
     }
+    ADP_TICK(4)
     double* ext_n = w.vecp((jn & 1) ? 7 : 2);      // exterior terms by ROW (summed in row order: results do not depend on list order)
+    ADP_NOUNROLL
     for (int r = tid; r < nr; r += nt) {
-      qm1_cur[r + 1] = cuj ? qm1_prev[r + 1] * eb1 : 0.;
-      ext_n[r + 1] = 0.;
-      if (kCst ? allowed_type(c, r + 1, jn) != 0 : pair_type(c.S[r + 1], c.S[jn]) != 0) w.cells[ex.atomic_inc(counter)] = (uint16_t)(r + 1);
+      const int i = r + 1;
+      qm1_cur[i] = cuj ? qm1_prev[i] * eb1 : 0.;
+      ext_n[i] = 0.;
+      const int type = kCst ? allowed_type(c, i, jn) : pair_type(c.S[i], c.S[jn]);
+      if (type != 0) {
+        w.cells[ex.atomic_inc(counter)] = (uint16_t)i;
+        // what the cell needs from the sequence alone is computed here, by a thread per row, instead of by one lane of the cell's group
+#if defined(ADP_X_NOHP)
+        hp[i] = 0.01; smv[i] = 0.5; sev[i] = 0.5 * q1[i - 1];
+#else
+        hp[i] = fast_hairpin<kCst>(c, H, G, w, motif_boltz, i, jn, type);
+        smv[i] = fast_stem_ml(c, H, w, type, i, jn);
+        sev[i] = fast_stem_ext(c, H, type, i, jn) * q1[i - 1];
+#endif
+      }
+    }
+    ADP_TICK(5)
+  };
+
+  // Qm(., jq) from the finished Qm1 column jq: row pairs (rows paired so that every pair sums the same number of terms), a few
+  // lanes per pair, a warp-sized chunk of pairs at a time from the queue.  Qm(., jq) is first read by column jq + 5.
+  auto drain_qm = [&](int jq) {
+    const int nrq = jq - 4;
+    if (nrq < 1) return;
+    const int npair = (nrq + 1) >> 1;
+    const int lgc = E::kSerial ? 0 : (nrq >= 24 ? 2 : 3);
+    const int Gc = 1 << lgc, per = E::kWarp >> lgc, subC = ex.lane() & (Gc - 1);
+    const int nchunk = (npair + per - 1) / per;
+    const double* qm1q = w.vecp(qm1_slot(jq));
+    int* ctr = w.qctr + ((jq + 1) & 1);
+    for (;;) {
+      const int ch = grab_chunk(ex, ctr);
+      if (ch >= nchunk) break;
+      const int slot = ch * per + (ex.lane() >> lgc);
+      const bool valid = slot < npair;
+      const int iA = slot + 1, iB = nrq - slot;       // iA <= iB; equal for the middle row of an odd count
+      double tA = 0., tB = 0.;
+      if (valid) {
+        tA = qm_row_terms(qm, qm1q, eMLbS, iA, nrq, kCst ? (int)c.upr[iA] : 1000, subC, Gc);
+        if (iB > iA) tB = qm_row_terms(qm, qm1q, eMLbS, iB, nrq, kCst ? (int)c.upr[iB] : 1000, subC, Gc);
+      }
+      ex.group_sum2_rt(tA, tB, Gc);
+      if (valid && subC == 0) {
+        qm[t4(iA, jq)] = tA + qm1q[iA];
+        if (iB > iA) qm[t4(iB, jq)] = tB + qm1q[iB];
+      }
     }
   };
 
+  for (int t = tid; t < 32; t += nt) w.lvoff[t] = 0;
   ex.sync();
   // j = 4 is a warm-up turn without cells: it only prepares column 5 (one call site keeps the code small)
   for (int j = 4; j <= n; j++) {
     const int nr = j - 4;                       // rows 1 .. nr
     const bool cuj = !kCst || can_unpair(c, j);
-    const double* qm1_prev = w.vecp((j - 1) & 1);
-    double* qm1_cur = w.vecp(j & 1);
+    const double* qm1_prev = w.vecp(qm1_slot(j - 1));
+    double* qm1_cur = w.vecp(qm1_slot(j));
     double* ext = w.vecp((j & 1) ? 7 : 2);
     const int m = w.counter[j & 1];
-    // ---- interval 1: Qb(i,j) for the listed cells, a lane group per cell
+    // ---- interval 1: Qb(i,j) for the listed cells, a lane group per cell; then deferred work
     {
-      if (tid == 0) w.counter[(j + 1) & 1] = 0;
+      if (tid == 0) { w.counter[(j + 1) & 1] = 0; w.qctr[(j + 1) & 1] = 0; }
+      ADP_NOUNROLL
+      for (int t = tid; t < 32; t += nt) {
+        // byte offsets of the row candidates of the level recursion of column j+1: level S reads Qb*FI(i+3, j+2-S)
+        const int S = 4 + (t >> 4) + 2 * (t & 15);
+        const int l = j + 2 - S;
+        w.lvoff[t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(double);
+      }
       const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const double* x1n_rd = w.vecp(4 + (j & 1));     // column j-2
@@ -368,32 +568,45 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         const bool valid = slot < m;
         const int i = valid ? w.cells[slot] : 1;
         double acc = 0.;
-        int type = 0;
         if (valid) {
           const int si = c.S[i], si1 = c.S[i + 1];
-          type = pair_type(si, sj);
+          const int type = pair_type(si, sj);
           const int codeij = (cn[i] << 4) | cpj;
           const int room = j - i - 6;                 // u1 + u2 <= room keeps the inner pair >= 4 apart
           int u1cap = kCst ? (int)c.upr[i + 1] : kMaxLoop, u2cap = upl_j1;
           if (u1cap > kMaxLoop) u1cap = kMaxLoop;
           if (u2cap > kMaxLoop) u2cap = kMaxLoop;
           double other = 0., accB = 0., acc1n = 0., accML = 0.;
-          if (sub == 0) {
-            other = fast_hairpin<kCst>(c, G, w, motif_boltz, i, j, type);
-            other += H.FI[codeij] * (gen0[i] + gen1[i]);
-          }
+          double cval = 0., ctab = 0.;
+          if (sub == 0) other = hp[i] + H.FI[codeij] * (gen0[i] + gen1[i]);
+          ADP_TICK(8)
           if (room >= 0) {
-            // corner candidates through the full tables
+            // corner candidates through the full tables, one per lane and round.  Software-pipelined and kept rolled (code size):
+            // the table load of a round is issued in that round and consumed in the next, the last one after the filters below.
+#if !defined(ADP_X_NOCORNER)
+            ADP_NOUNROLL
             for (int q = sub; q < 9; q += Gs) {
               int u1, u2;
               corner_u(q, &u1, &u2);
+              double v2 = 0.;
+              const double* p2 = zp;
               if (u1 <= u1cap && u2 <= u2cap && u1 + u2 <= room) {
                 const int k = i + 1 + u1, l = j - 1 - u2;
                 const double v = qb[t4(k, l)] * H.RI[(cn[l] << 4) | cp[k]];
-                if (v != 0.)
-                  other += v * w.scaleG[u1 + u2 + 2] * interior_x(*G, G, u1, u2, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1]);
+                if (v != 0.) {
+                  double fac;
+                  p2 = corner_entry(H, G, q, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1], &fac);
+                  v2 = v * fac;
+                }
               }
+              const double t2 = *p2;
+              other += cval * ctab;
+              cval = v2;
+              ctab = t2;
             }
+#endif
+            ADP_TICK(9)
+#if !defined(ADP_X_NOAXIS)
             // bulges with the unpaired run on the 3' side: k = i+1, l = j-1-u2, u2 >= 2
             {
               const int hi = room < u2cap ? room : u2cap;
@@ -426,8 +639,11 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               const double* xn = x1n_rd + i + 1;
               for (int u1 = 3 + sub; u1 <= hi; u1 += Gs) acc1n += xn[u1] * H.tap1n[u1];
             }
+#endif
           }
+          ADP_TICK(10)
           // multiloop closed by (i,j): Qm(i+1,k-1) * Qm1(k,j-1), k = i+6 .. j-5
+#if !defined(ADP_X_NOML)
           {
             int k = i + 6 + sub;
             int off = t4(i + 1, k - 1);
@@ -441,22 +657,31 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               pq += Gs;
             }
           }
+#endif
+          // ---- cell total
+          other += cval * ctab;
           acc = other + au_factor(H, si, sj) * accB + H.F1n[codeij] * acc1n + accML * (H.MLclosing * H.FM[codeij] * H.scale2);
         }
+        ADP_TICK(11)
         acc = ex.group_sum_rt(acc, Gs);
+        ADP_TICK(12)
         if (valid && sub == 0) {
           qb[t4(i, j)] = (i > 1 && j < n) ? acc * H.FI[(cn[j] << 4) | cp[i]] : acc;     // stored premultiplied
-          qm1_cur[i] += acc * fast_stem_ml(c, H, G, w, type, i, j);
-          ext[i] = acc * fast_stem_ext(c, G, type, i, j) * q1[i - 1];
+          qm1_cur[i] += acc * smv[i];
+          ext[i] = acc * sev[i];
         }
+        ADP_TICK(13)
       }
+      ADP_TICK(0)
     }
     ex.sync();
-    // ---- interval 2: premultiplied vectors of the new column; Qm(i,j) for every row (rows paired so that every
-    //      lane group sums the same number of terms); exterior prefix; preparation of column j+1
+    ADP_TICK(2)
+    // ---- interval 2: premultiplied vectors of the new column; exterior prefix; preparation of column j+1; what is left
+    //      of the deferred work
     {
       double* x1n_wr = w.vecp(4 + (j & 1));
       const int cnj = cn[j] << 4;
+      ADP_NOUNROLL
       for (int r = tid; r < nr; r += nt) {
         const int i = r + 1;
         const double v = qb[t4(i, j)];                  // Qb * FI; rows / columns at the sequence ends are never read back
@@ -464,34 +689,24 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         xA[i] = v * H.RB[code];
         x1n_wr[i] = v * H.R1[code];
       }
-      const int npair = (nr + 1) >> 1;
-      const int lg = group_lg(npair, nt_lg, warp_lg);
-      const int Gc = 1 << lg, slotsC = nt >> lg, subC = tid & (Gc - 1);
-      for (int slot0 = 0; slot0 < npair; slot0 += slotsC) {
-        const int slot = slot0 + (tid >> lg);
-        const bool valid = slot < npair;
-        const int iA = slot + 1, iB = nr - slot;       // iA <= iB; equal for the middle row of an odd count
-        double tA = 0., tB = 0.;
-        if (valid) {
-          tA = qm_row_terms(qm, qm1_cur, eMLbS, iA, nr, kCst ? (int)c.upr[iA] : 1000, subC, Gc);
-          if (iB > iA) tB = qm_row_terms(qm, qm1_cur, eMLbS, iB, nr, kCst ? (int)c.upr[iB] : 1000, subC, Gc);
-        }
-        ex.group_sum2_rt(tA, tB, Gc);
-        if (valid && subC == 0) {
-          qm[t4(iA, j)] = tA + qm1_cur[iA];
-          if (iB > iA) qm[t4(iB, j)] = tB + qm1_cur[iB];
-        }
-      }
       if (ex.warp() == 0) {
         double e = 0.;
+        ADP_NOUNROLL
         for (int s = 1 + ex.lane(); s <= nr; s += E::kWarp) e += ext[s];
         e = ex.warp_sum(e);
         if (ex.lane() == 0) q1[j] = (cuj ? q1[j - 1] * s1 : 0.) + e;
       }
+      ADP_TICK(3)
       if (j < n) prepare_column(j + 1);
+#if !defined(ADP_X_NOQM)
+      drain_qm(j - 1);
+#endif
+      ADP_TICK(6)
     }
     ex.sync();
+    ADP_TICK(7)
   }
+  ADP_PROF_REPORT("inside ")
   return q1[n];
 }
 
@@ -499,9 +714,9 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
 // outside pass.  Overwrites Qb column by column (l = n .. 5) with the outside weights; the probabilities of a
 // column go to `bppm` / the pair queries as soon as the column is complete.
 // vector roles: 0 A(i,l) (multiloop carrier with >= 1 stem right of l), 1 B(i,l) (nothing right of l),
-// 2 and 16 P(.,l) of the finished column by parity, 3 xA (Pout * terminal factor, column l+1), 4/5 x1n (by column
-// parity), 6/7/8 xI (by column mod 3), 9 q1, 10 eMLb powers, 11/12 generic sums, 13 qln, 14 exterior-suffix
-// accumulators, 15 bound-motif probabilities per site.
+// 2 and 6 P(.,l) of the finished column by parity, 3 xA (Pout * terminal factor, column l+1), 4/5 x1n (by column
+// parity), 8 exterior stem factor of the cells of the column being prepared, 9 q1, 10 eMLb powers, 11/12 generic sums, 13 qln,
+// 14 exterior-suffix accumulators, 15 bound-motif probabilities per site.
 struct FastOut {
   double* bppm;          // NULL or n(n+1)/2 doubles, row-major upper triangle incl. diagonal, 0-based
   int n_query;
@@ -526,9 +741,10 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   const uint8_t* const cn = w.cn;
   const uint8_t* const cp = w.cp;
   for (int k = tid; k < kFastVectors * ld; k += nt)
-    if (k < 9 * ld || (k >= 11 * ld && k < 13 * ld) || k >= 14 * ld) w.vbase[k] = 0.;
+    if (k < 9 * ld || k >= 11 * ld) w.vbase[k] = 0.;
   double* const vA = w.vecp(0);
   double* const vB = w.vecp(1);
+  double* const sxv = w.vecp(8);
   double* const xA = w.vecp(3);
   const double* const q1 = w.vecp(9);
   const double* const eMLbS = w.vecp(10);
@@ -545,9 +761,11 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   double d[kFastLevels];
   const double* const zp = &H.pad;
   ADP_LEVEL_ZERO()
+  ADP_PROF_DECL
   if (mem_state)
     for (int k = tid; k < 2 * R * kFastLevels; k += nt) w.dstate[k] = 0.;
   if (tid == 0) { w.counter[0] = 0; w.counter[1] = 0; }
+  for (int t = tid; t < 32; t += nt) w.lvoff[t] = 0;
   ex.sync();
   if (tid == 0) { qln[n + 1] = 1.; qln[n + 2] = 0.; }
   const double Z = q1[n];
@@ -607,24 +825,31 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       if (key < ln + 1) key += R;
       const int k = key - ln;
       if (k >= 1 && k <= nr) {
-        int smax = (k - 2) + (n - ln - 1);          // u1 <= k-2, u2 <= n-ln-1
-        if (smax > kMaxLoop) smax = kMaxLoop;
+        int sm = (k - 2) + (n - ln - 1);            // u1 <= k-2, u2 <= n-ln-1
+        if (sm > kMaxLoop) sm = kMaxLoop;
+        sm -= par;                                  // level Q is on iff 4 + 2Q <= sm
         double gen = 0.;
-        if (k >= 4 && ln + 3 <= n && smax >= 4) {
+        if (k >= 4 && ln + 3 <= n && sm + par >= 4) {
           const int upl_k1 = kCst ? (int)c.upl[k - 1] : 1000;
           const bool g = upl_k1 >= 1 && upr_l1 >= 1;
           const bool ok1 = upl_k1 >= 2, ok2 = upr_l1 >= 2;
-          const double* qrow = qb + k - 4;           // Pout*FI(k-3, j) = qrow[(j-4)(j-5)/2]
-          const double* xi = col3 + k;               // xi[-S] = Pout*FI(k+1-S, ln+3)
-          const int room1 = n + 1 - ln;              // border 1 needs j = ln+S-1 <= n
-#define ADP_P1 (qrow + (((ln + S - 5) * (ln + S - 6)) >> 1))
-#define ADP_C1 (S <= room1 && (!kCst || (ok1 && upr_l1 >= S - 2)))
-#define ADP_P2 (xi - S)
-#define ADP_C2 (S <= k && (!kCst || (ok2 && upl_k1 >= S - 2)))
-          if (par) { ADP_LEVEL_PASS(1, ADP_P1, ADP_C1, ADP_P2, ADP_C2) } else { ADP_LEVEL_PASS(0, ADP_P1, ADP_C1, ADP_P2, ADP_C2) }
-#undef ADP_P1
+          const int room1 = n + 1 - ln - par;        // row candidate needs j = ln+S-1 <= n
+          const int room2 = k - par;                 // column candidate needs i = k+1-S >= 1
+          const int sm1 = sm < room1 ? sm : room1, sm2 = sm < room2 ? sm : room2;
+          const int lim1 = upr_l1 - par - 2, lim2 = upl_k1 - par - 2;     // constraint gates: S - 2 unpaired bases on the other side
+          const char* qrow = reinterpret_cast<const char*>(qb + k - 4);   // Pout*FI(k-3, j) = qrow[(j-4)(j-5)/2], j = ln+S-1: offset from the table
+          const double* xi = col3 + k - par - 4;     // Pout*FI(k+1-S, ln+3) = xi[-2Q]
+          const double* fcn = ADP_FC.nin + (par << 4);
+          const double* fci = ADP_FC.ip + (par << 4);
+          ADP_LEVEL_OFFSETS(w.lvoff + (par << 4))
+#define ADP_A1(Q) reinterpret_cast<const double*>(qrow + lo[Q])
+#define ADP_C1(Q) (!kCst || (ok1 && 2 * (Q) <= lim1))
+#define ADP_A2(Q) (xi - 2 * (Q))
+#define ADP_C2(Q) (!kCst || (ok2 && 2 * (Q) <= lim2))
+          ADP_LEVEL_PASS(ADP_A1, ADP_C1, ADP_A2, ADP_C2)
+#undef ADP_A1
 #undef ADP_C1
-#undef ADP_P2
+#undef ADP_A2
 #undef ADP_C2
         } else {
           ADP_LEVEL_ZERO()
@@ -634,23 +859,38 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       if (mem_state)
         for (int q = 0; q < kFastLevels; q++) w.dstate[(size_t)task * kFastLevels + q] = d[q];
     }
+    ADP_TICK(4)
     // (d) the cells of this column that carry weight; the column's probability vector starts at zero
     double* pcol = w.vecp((ln & 1) ? 6 : 2);
     int* counter = w.counter + (ln & 1);
+    ADP_NOUNROLL
     for (int r = tid; r < nr; r += nt) {
-      pcol[r + 1] = 0.;
-      if (qb[t4(r + 1, ln)] != 0.) w.cells[ex.atomic_inc(counter)] = (uint16_t)(r + 1);
+      const int k = r + 1;
+      pcol[k] = 0.;
+      if (qb[t4(k, ln)] != 0.) {
+        w.cells[ex.atomic_inc(counter)] = (uint16_t)k;
+        sxv[k] = fast_stem_ext(c, H, pair_type(c.S[k], c.S[ln]), k, ln);      // by a thread per row instead of one lane of the cell's group
+      }
     }
+    ADP_TICK(5)
   };
 
+  ADP_TICK(1)
   // l = n+1 is a warm-up turn without cells: it only prepares column n (one call site keeps the code small)
   for (int l = n + 1; l >= kTurn + 2; l--) {
     const int nr = l <= n ? l - 4 : 0;          // rows k = 1 .. nr
     double* pcol = w.vecp((l & 1) ? 6 : 2);
     const int m = l <= n ? w.counter[l & 1] : 0;
-    // ---- interval 1: outside weight of every listed pair (k,l)
+    // ---- interval 1: outside weight of every listed pair (k,l); then deferred work
     {
       if (tid == 0) w.counter[(l + 1) & 1] = 0;
+      ADP_NOUNROLL
+      for (int t = tid; t < 32; t += nt) {
+        // byte offsets of the row candidates of the level recursion of column l-1: level S reads Pout*FI(k-3, l+S-2)
+        const int S = 4 + (t >> 4) + 2 * (t & 15);
+        const int j = l + S - 2;
+        w.lvoff[t] = (((j - 4) * (j - 5)) >> 1) * (int)sizeof(double);
+      }
       const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const int gstep = (Gs * (Gs - 1)) >> 1;
@@ -676,22 +916,32 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           if (u1cap > kMaxLoop) u1cap = kMaxLoop;
           if (u1cap > k - 2) u1cap = k - 2;                     // i = k-1-u1 >= 1
           double other = 0., accB = 0., acc1n = 0., accML = 0.;
-          if (sub == 0) {
-            other = q1[k - 1] * extl * fast_stem_ext(c, G, type, k, l);
-            other += H.FI[codekl] * (gen0[k] + gen1[k]);
-          }
+          double cval = 0., ctab = 0.;
+          if (sub == 0) other = q1[k - 1] * extl * sxv[k] + H.FI[codekl] * (gen0[k] + gen1[k]);
+          ADP_TICK(8)
           if (k >= 2 && l < n) {
             const int t2r = rtype(type);
-            for (int q = sub; q < 9; q += Gs) {
+            ADP_NOUNROLL
+            for (int q = sub; q < 9; q += Gs) {       // software-pipelined like the inside pass
               int u1, u2;
               corner_u(q, &u1, &u2);
+              double v2 = 0.;
+              const double* p2 = zp;
               if (u1 <= u1cap && u2 <= u2cap) {
                 const int i = k - 1 - u1, j = l + 1 + u2;
                 const double v = qb[t4(i, j)] * H.RI[(cn[i] << 4) | cp[j]];
-                if (v != 0.)
-                  other += v * w.scaleG[u1 + u2 + 2] * interior_x(*G, G, u1, u2, pair_type(c.S[i], c.S[j]), t2r, c.S[i + 1], c.S[j - 1], sp1, sq1);
+                if (v != 0.) {
+                  double fac;
+                  p2 = corner_entry(H, G, q, pair_type(c.S[i], c.S[j]), t2r, c.S[i + 1], c.S[j - 1], sp1, sq1, &fac);
+                  v2 = v * fac;
+                }
               }
+              const double t2 = *p2;
+              other += cval * ctab;
+              cval = v2;
+              ctab = t2;
             }
+            ADP_TICK(9)
             // enclosing bulges with the run on the 3' side: i = k-1, j = l+1+u2, u2 >= 2
             {
               const int cni = cn[k - 1] << 4;
@@ -726,6 +976,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
               const double* xn = x1n_rd + k - 1;
               for (int u1 = 3 + sub; u1 <= hi; u1 += Gs) acc1n += xn[-u1] * H.tap1n[u1];
             }
+            ADP_TICK(10)
             // (k,l) is a stem of a multiloop closed by (i,j), i < k, j > l:  u = k-1-i unpaired bases left of k
             {
               const double* qcol = qm + t4(1, k - 1) - 1;       // Qm(i+1,k-1) = qcol[i+1], valid for i+1 <= k-5
@@ -738,25 +989,33 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
               }
             }
           }
+          // ---- cell total
+          other += cval * ctab;
           val = other + au_factor(H, sk, sl) * accB + H.F1n[codekl] * acc1n;
           if (k >= 2 && l < n) val += accML * (H.FM[codekl] * H.scale2);
         }
+        ADP_TICK(11)
         val = ex.group_sum_rt(val, Gs);
+        ADP_TICK(12)
         if (valid && sub == 0) {
           const int idx = t4(k, l);
           const double qbv = (k > 1 && l < n) ? qb[idx] * H.RI[cnl | cp[k]] : qb[idx];     // back to the plain Qb(k,l)
           pcol[k] = val * qbv;
-          accq[k] += qbv * fast_stem_ext(c, G, type, k, l) * qln[l + 1];
-          if (has_motif && is_motif_site(c, k, l)) pm[k] = val * fast_hairpin<kCst>(c, G, w, motif_boltz, k, l, type);
+          accq[k] += qbv * sxv[k] * qln[l + 1];
+          if (has_motif && is_motif_site(c, k, l)) pm[k] = val * fast_hairpin<kCst>(c, H, G, w, motif_boltz, k, l, type);
           qb[idx] = val * H.FI[(cn[k] << 4) | cp[l]];       // outside weight, premultiplied (outer orientation)
         }
+        ADP_TICK(13)
       }
+      ADP_TICK(0)
     }
     ex.sync();
+    ADP_TICK(2)
     // ---- interval 2: premultiplied vectors of the finished column; results; preparation of column l-1
     {
       double* x1n_wr = w.vecp(4 + (l & 1));
       const int cpl = cp[l];
+      ADP_NOUNROLL
       for (int r = tid; r < nr + 3; r += nt) {
         const int k = r + 1;
         double v = 0.;
@@ -766,6 +1025,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         x1n_wr[k] = v * H.R1[code];
       }
       if (out.bppm)
+        ADP_NOUNROLL
         for (int r = tid; r < nr; r += nt)
           if (pcol[r + 1] != 0.) out.bppm[bppm_index(n, r + 1, l)] = pcol[r + 1];
       for (int q = tid; q < out.n_query; q += nt) {
@@ -773,10 +1033,14 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         if (a > b) { const int t = a; a = b; b = t; }
         if (b + 1 == l && a >= 0 && a + 1 <= nr) out.qprobs[q] = pcol[a + 1];
       }
+      ADP_TICK(3)
       if (l > kTurn + 2) prepare_column(l - 1);
+      ADP_TICK(6)
     }
     ex.sync();
+    ADP_TICK(7)
   }
+
   // the motif's inner pairs inherit the probability of the bound hairpin
   if (has_motif && tid == 0) {
     for (int i = 1; i + motif->len - 1 <= n; i++) {
@@ -793,6 +1057,8 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     }
   }
   ex.sync();
+  ADP_TICK(6)
+  ADP_PROF_REPORT("outside")
 }
 
 }  // namespace adp

@@ -1,0 +1,20 @@
+"""Lock-step check: one job per CTA (296 jobs) against a long queue (tuning; ADDAPT_B200_LIB selects a variant build)."""
+import sys, time
+sys.path.insert(0, '.')
+import torch
+import addapt_b200
+from tests import cases
+eng = addapt_b200.Engine(0)
+for B in (148, 8192):
+    seqs = cases.templated_designs(B, 1, n=100)
+    a = torch.from_numpy(addapt_b200.capi.seqs_to_array(seqs)).cuda()
+    dg = torch.zeros(B, 2, dtype=torch.float64, device='cuda')
+    d1 = torch.zeros(B, dtype=torch.float64, device='cuda')
+    for rep in range(3):
+        torch.cuda.synchronize(); t0 = time.time()
+        eng.fold_eval_raw(B, 100, a, cases.THEO, 0, None, None, dg, None)
+        torch.cuda.synchronize(); t1 = time.time()
+        eng.pf_raw(B, 100, a, d1)
+        torch.cuda.synchronize(); t2 = time.time()
+    rounds_fe = -(-2 * B // 296); rounds_in = -(-B // 296)
+    print("%s B=%d: fold-eval job %.3f ms/round, inside job %.3f ms/round" % (sys.argv[1], B, 1e3 * (t1 - t0) / rounds_fe, 1e3 * (t2 - t1) / rounds_in))
