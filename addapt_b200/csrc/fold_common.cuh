@@ -227,14 +227,15 @@ ADP_HD void load_context(const E& ex, SeqCtx& c, const uint8_t* seq, const Const
 // carving a raw (shared-memory) buffer into the per-construct arrays
 struct Carver {
   char* p;
-  ADP_HD explicit Carver(void* base) : p((char*)base) {}
+  size_t off;
+  ADP_HD explicit Carver(void* base) : p((char*)base), off((16 - ((size_t)base & 15)) & 15) {}
   // 16-byte aligned array of `count` T.  Only pointer arithmetic on `p` (no integer -> pointer cast), so that the
   // compiler keeps the address space of the buffer (shared memory loads instead of generic ones).
   template <class T>
   ADP_HD T* take(size_t count) {
-    p += (16 - ((size_t)p & 15)) & 15;
-    T* r = reinterpret_cast<T*>(p);
-    p += count * sizeof(T);
+    off = (off + 15) & ~(size_t)15;
+    T* r = reinterpret_cast<T*>(p + off);
+    off += count * sizeof(T);
     return r;
   }
 };

@@ -607,37 +607,31 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
 #endif
             ADP_TICK(9)
 #if !defined(ADP_X_NOAXIS)
-            // bulges with the unpaired run on the 3' side: k = i+1, l = j-1-u2, u2 >= 2
+            // The four 1-D filters along the loop's axes, fused into one loop so that their load chains overlap:
+            //   bulges with the unpaired run on the 3' side (k = i+1, l = j-1-u, u >= 2) and on the 5' side (l = j-1, k = i+1+u:
+            //   premultiplied column vector xA);  1 x u loops (k = i+2, l = j-1-u, u >= 3) and u x 1 loops (l = j-2, k = i+1+u:
+            //   column vector x1n).  tap1n[2] = 0.  A term beyond its own limit is selected away after the (always valid) loads.
             {
-              const int hi = room < u2cap ? room : u2cap;
-              const int cpk = cp[i + 1];
-              for (int u2 = 2 + sub; u2 <= hi; u2 += Gs) {
-                const int l = j - 1 - u2;
-                accB += qb[t4(i + 1, l)] * H.RB[(cn[l] << 4) | cpk] * H.tapB[u2];
-              }
-            }
-            // 1 x u2 loops: k = i+2, u2 >= 3
-            if (u1cap >= 1) {
-              int hi = room - 1 < u2cap ? room - 1 : u2cap;
-              if (hi > kMaxLoop - 1) hi = kMaxLoop - 1;
-              const int cpk = cp[i + 2];
-              for (int u2 = 3 + sub; u2 <= hi; u2 += Gs) {
-                const int l = j - 1 - u2;
-                acc1n += qb[t4(i + 2, l)] * H.R1[(cn[l] << 4) | cpk] * H.tap1n[u2];
-              }
-            }
-            // bulges with the run on the 5' side: l = j-1, k = i+1+u1, u1 >= 2 -- premultiplied column vector
-            {
-              const int hi = room < u1cap ? room : u1cap;
+              const int hiB3 = room < u2cap ? room : u2cap;
+              const int hiB5 = room < u1cap ? room : u1cap;
+              int hi13 = room - 1 < u2cap ? room - 1 : u2cap, hi31 = room - 1 < u1cap ? room - 1 : u1cap;
+              if (hi13 > kMaxLoop - 1) hi13 = kMaxLoop - 1;
+              if (hi31 > kMaxLoop - 1) hi31 = kMaxLoop - 1;
+              if (u1cap < 1) hi13 = -1;
+              if (u2cap < 1) hi31 = -1;
+              const int hmax = hiB3 > hiB5 ? hiB3 : hiB5;
+              const int cpk1 = cp[i + 1], cpk2 = cp[i + 2];
               const double* xa = xA + i + 1;
-              for (int u1 = 2 + sub; u1 <= hi; u1 += Gs) accB += xa[u1] * H.tapB[u1];
-            }
-            // u1 x 1 loops: l = j-2, u1 >= 3
-            if (u2cap >= 1) {
-              int hi = room - 1 < u1cap ? room - 1 : u1cap;
-              if (hi > kMaxLoop - 1) hi = kMaxLoop - 1;
               const double* xn = x1n_rd + i + 1;
-              for (int u1 = 3 + sub; u1 <= hi; u1 += Gs) acc1n += xn[u1] * H.tap1n[u1];
+              for (int u = 2 + sub; u <= hmax; u += Gs) {
+                const int l = j - 1 - u;                       // >= i + 5: (i+1,l) is a cell; (i+2,l) is one unless u = room
+                const int cl = cn[l] << 4;
+                const double* pb = qb + t4(i + 1, l);
+                const double b3 = pb[0] * H.RB[cl | cpk1], n3 = pb[1] * H.R1[cl | cpk2];
+                const double b5 = xa[u], n5 = xn[u];
+                accB += H.tapB[u] * ((u <= hiB3 ? b3 : 0.) + (u <= hiB5 ? b5 : 0.));
+                acc1n += H.tap1n[u] * ((u <= hi13 ? n3 : 0.) + (u <= hi31 ? n5 : 0.));
+              }
             }
 #endif
           }
@@ -780,7 +774,11 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     // (a) exterior suffix Q(ln,n): position ln unpaired, or paired with some l' >= ln+4 (already accumulated)
     if (tid == 0) qln[ln] = ((!kCst || can_unpair(c, ln)) ? qln[ln + 1] * s1 : 0.) + accq[ln];
     // (b) multiloop carriers for every possible 5' closing position i <= ln-5
+#if defined(ADP_X_OUT_NOCARRIER)
+    if (false) {
+#else
     if (ln < n) {
+#endif
       const int nrow = ln - 5;
       const bool cul1 = !kCst || can_unpair(c, ln + 1);
       const int lg = group_lg(nrow > 0 ? nrow : 1, nt_lg, warp_lg);
@@ -829,7 +827,11 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         if (sm > kMaxLoop) sm = kMaxLoop;
         sm -= par;                                  // level Q is on iff 4 + 2Q <= sm
         double gen = 0.;
+#if defined(ADP_X_OUT_NOLEVELS)
+        if (false) {
+#else
         if (k >= 4 && ln + 3 <= n && sm + par >= 4) {
+#endif
           const int upl_k1 = kCst ? (int)c.upl[k - 1] : 1000;
           const bool g = upl_k1 >= 1 && upr_l1 >= 1;
           const bool ok1 = upl_k1 >= 2, ok2 = upr_l1 >= 2;
@@ -893,7 +895,6 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       }
       const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
-      const int gstep = (Gs * (Gs - 1)) >> 1;
       const double* x1n_rd = w.vecp(4 + (l & 1));        // column l+2
       const int upr_l1 = kCst ? (int)c.upr[l + 1] : n - l;
       const int sl = c.S[l], sq1 = c.S[l + 1], cnl = cn[l] << 4;
@@ -921,6 +922,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           ADP_TICK(8)
           if (k >= 2 && l < n) {
             const int t2r = rtype(type);
+#if !defined(ADP_X_OUT_NOCORNER)
             ADP_NOUNROLL
             for (int q = sub; q < 9; q += Gs) {       // software-pipelined like the inside pass
               int u1, u2;
@@ -941,42 +943,36 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
               cval = v2;
               ctab = t2;
             }
+#endif
             ADP_TICK(9)
-            // enclosing bulges with the run on the 3' side: i = k-1, j = l+1+u2, u2 >= 2
+#if !defined(ADP_X_OUT_NOAXIS)
+            // enclosing bulges with the run on the 3' side: i = k-1, j = l+1+u2, u2 >= 2 -- the four 1-D filters fused into one
+            // loop like in the inside pass: enclosing bulges (i = k-1, j = l+1+u / j = l+1, i = k-1-u: column vector xA), enclosing
+            // 1 x u loops (i = k-2, j = l+1+u, u >= 3) and u x 1 loops (j = l+2, i = k-1-u: column vector x1n).
             {
-              const int cni = cn[k - 1] << 4;
-              int u2 = 2 + sub;
-              int off = t4(k - 1, l + 1 + u2);
-              for (; u2 <= u2cap; u2 += Gs) {
-                const int j = l + 1 + u2;
-                accB += qb[off] * H.RB[cni | cp[j]] * H.tapB[u2];
-                off += Gs * (j - 4) + gstep;
-              }
-            }
-            // enclosing 1 x u2 loops: i = k-2, u2 >= 3
-            if (u1cap >= 1) {
-              const int hi = u2cap < kMaxLoop - 1 ? u2cap : kMaxLoop - 1;
-              const int cni = cn[k - 2] << 4;
-              int u2 = 3 + sub;
-              int off = t4(k - 2, l + 1 + u2);
-              for (; u2 <= hi; u2 += Gs) {
-                const int j = l + 1 + u2;
-                acc1n += qb[off] * H.R1[cni | cp[j]] * H.tap1n[u2];
-                off += Gs * (j - 4) + gstep;
-              }
-            }
-            // run on the 5' side: j = l+1, i = k-1-u1, u1 >= 2 -- premultiplied column vector
-            {
+              int hi13 = u2cap < kMaxLoop - 1 ? u2cap : kMaxLoop - 1, hi31 = u1cap < kMaxLoop - 1 ? u1cap : kMaxLoop - 1;
+              if (u1cap < 1) hi13 = -1;
+              if (u2cap < 1) hi31 = -1;
+              const int hmax = u2cap > u1cap ? u2cap : u1cap;
+              const int cni1 = cn[k - 1] << 4, cni2 = k >= 3 ? cn[k - 2] << 4 : 0;
               const double* xa = xA + k - 1;
-              for (int u1 = 2 + sub; u1 <= u1cap; u1 += Gs) accB += xa[-u1] * H.tapB[u1];
-            }
-            // u1 x 1 loops: j = l+2
-            if (u2cap >= 1) {
-              const int hi = u1cap < kMaxLoop - 1 ? u1cap : kMaxLoop - 1;
               const double* xn = x1n_rd + k - 1;
-              for (int u1 = 3 + sub; u1 <= hi; u1 += Gs) acc1n += xn[-u1] * H.tap1n[u1];
+              for (int u = 2 + sub; u <= hmax; u += Gs) {
+                const bool in3 = u <= u2cap;                   // j = l+1+u <= n
+                const int j = l + 1 + (in3 ? u : 0);
+                const int cj = cp[j];
+                const double* pb = in3 ? qb + t4(k - 1, j) : zp;       // (k-1,j) is a cell; (k-2,j) is the one before it when k >= 3
+                const double b3 = pb[0] * H.RB[cni1 | cj];
+                const double n3 = u <= hi13 ? pb[-1] * H.R1[cni2 | cj] : 0.;
+                const int ub = u <= u1cap ? u : 0;             // row k-1-u >= 1
+                const double b5 = xa[-ub], n5 = xn[-ub];
+                accB += H.tapB[u] * ((in3 ? b3 : 0.) + (u <= u1cap ? b5 : 0.));
+                acc1n += H.tap1n[u] * (n3 + (u <= hi31 ? n5 : 0.));
+              }
             }
+#endif
             ADP_TICK(10)
+#if !defined(ADP_X_OUT_NOML)
             // (k,l) is a stem of a multiloop closed by (i,j), i < k, j > l:  u = k-1-i unpaired bases left of k
             {
               const double* qcol = qm + t4(1, k - 1) - 1;       // Qm(i+1,k-1) = qcol[i+1], valid for i+1 <= k-5
@@ -988,6 +984,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
                 accML += t;
               }
             }
+#endif
           }
           // ---- cell total
           other += cval * ctab;
