@@ -227,10 +227,25 @@ ADP_HD void load_context(const E& ex, SeqCtx& c, const uint8_t* seq, const Const
 // carving a raw (shared-memory) buffer into the per-construct arrays
 struct Carver {
   char* p;
-  size_t off;
-  ADP_HD explicit Carver(void* base) : p((char*)base), off((16 - ((size_t)base & 15)) & 15) {}
+  ADP_HD explicit Carver(void* base) : p((char*)base) {}
   // 16-byte aligned array of `count` T.  Only pointer arithmetic on `p` (no integer -> pointer cast), so that the
   // compiler keeps the address space of the buffer (shared memory loads instead of generic ones).
+  template <class T>
+  ADP_HD T* take(size_t count) {
+    p += (16 - ((size_t)p & 15)) & 15;
+    T* r = reinterpret_cast<T*>(p);
+    p += count * sizeof(T);
+    return r;
+  }
+};
+
+// Same layout, but every array is the (aligned) base plus an offset that is tracked as an integer: with many arrays live
+// (the fast PF path) the compiler then rebuilds addresses from one base register instead of carrying a pointer per array
+// (measured: PF fast +10 %; the MFE kernel, with fewer arrays, is faster with Carver).
+struct OffsetCarver {
+  char* p;
+  size_t off;
+  ADP_HD explicit OffsetCarver(void* base) : p((char*)base), off((16 - ((size_t)base & 15)) & 15) {}
   template <class T>
   ADP_HD T* take(size_t count) {
     off = (off + 15) & ~(size_t)15;
@@ -245,15 +260,16 @@ ADP_HD size_t ctx_bytes(int n) {
   return 16 * 8 + (size_t)(n + 4) * (1 + 1 + 1) + (size_t)(n + 4) * 2 * 4;
 }
 
-ADP_HD void carve_ctx(Carver& cv, SeqCtx& c, int n) {
+template <class CV>
+ADP_HD void carve_ctx(CV& cv, SeqCtx& c, int n) {
   c.n = n;
-  c.S = cv.take<uint8_t>(n + 4);
-  c.flag = cv.take<uint8_t>(n + 4);
-  c.motif_at = cv.take<uint8_t>(n + 4);
-  c.partner = cv.take<uint16_t>(n + 4);
-  c.enc = cv.take<uint16_t>(n + 4);
-  c.upr = cv.take<uint16_t>(n + 4);
-  c.upl = cv.take<uint16_t>(n + 4);
+  c.S = cv.template take<uint8_t>(n + 4);
+  c.flag = cv.template take<uint8_t>(n + 4);
+  c.motif_at = cv.template take<uint8_t>(n + 4);
+  c.partner = cv.template take<uint16_t>(n + 4);
+  c.enc = cv.template take<uint16_t>(n + 4);
+  c.upr = cv.template take<uint16_t>(n + 4);
+  c.upl = cv.template take<uint16_t>(n + 4);
 }
 
 ADP_HD bool is_motif_site(const SeqCtx& c, int i, int j) { return c.motif_len > 0 && (j - i + 1) == c.motif_len && c.motif_at[i]; }

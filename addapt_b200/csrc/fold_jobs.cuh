@@ -90,7 +90,7 @@ ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats)
 template <class E>
 ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* mats, double* dstate = nullptr, double* qm_ext = nullptr) {
   const int n = job.n;
-  Carver cv(small);
+  OffsetCarver cv(small);
   PfHot* H = cv.take<PfHot>(1);
   SeqCtx c;
   carve_ctx(cv, c, n);
