@@ -90,6 +90,9 @@ ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats)
 template <class E>
 ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* mats, double* dstate = nullptr, double* qm_ext = nullptr) {
   const int n = job.n;
+#if defined(ADP_PHASE_PROFILE) && defined(__CUDA_ARCH__)
+  const long long tp0_ = clock64();
+#endif
   OffsetCarver cv(small);
   PfHot* H = cv.take<PfHot>(1);
   SeqCtx c;
@@ -121,6 +124,9 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   fast_special_hairpins(ex, c, job.T, w);
   ex.sync();
   if (w.counter[2]) return false;
+#if defined(ADP_PHASE_PROFILE) && defined(__CUDA_ARCH__)
+  if (blockIdx.x == 0 && threadIdx.x == 0) printf("prologue %lld cycles\n", clock64() - tp0_);
+#endif
 
   const double Z = c.has_cst ? fast_inside<true>(ex, c, *H, job.T, mboltz, w) : fast_inside<false>(ex, c, *H, job.T, mboltz, w);
   if (ex.tid() == 0)

@@ -64,7 +64,7 @@ constexpr int kFastLevels = 14;       // level sums per thread: s = 4+par, 6+par
 constexpr int kFastMaxN = 320;        // longest construct the fast path takes (ADP_MAX_LEN)
 
 struct PfHot {                        // shared memory, staged once per CTA
-  double FI[256], F1n[256], FM[256];  // mismatch_interior, mismatch_interior_1n, multiloop stem factor (closing orientation)
+  double FI[256], FM[256];            // mismatch_interior, multiloop stem factor (closing orientation); mismatch_interior_1n = R1 * FI
   // The matrices hold Qb (inside) / the outside weight PREMULTIPLIED by FI of the pair (inner orientation inside, outer
   // orientation outside), so that the level recursion reads its candidates with one load.  Ratios for the other readers:
   double RI[256], RB[256], R1[256], RM[256];   // 1/FI, terminal-AU factor / FI, F1n / FI, FM / FI  (0 for non-pairs)
@@ -74,7 +74,7 @@ struct PfHot {                        // shared memory, staged once per CTA
   // what hairpins, stems at the sequence ends, exterior stems and the corner candidates read: staged so that no L2-latency
   // load sits on the path of a cell (only int11 / int21 / int22 and the special-hairpin weights stay in global memory)
   double stack[64];                   // [type][type2]
-  double mm23[200], mmH[200], mmExt[200];     // [type][5' side neighbour][3' side neighbour]
+  double mm23[96], mmH[96], mmExt[96];        // [type 1..6][5' side neighbour 1..4][3' side neighbour 1..4], see mm_index
   double dangle5[40], dangle3[40];
   double cfac[16];                    // per corner candidate q: scale[u1+u2+2] * (bulge[1] | interior[5] * ninio[1] | 1)
   double one, MLintern;
@@ -111,6 +111,9 @@ ADP_HD void corner_u(int q, int* u1, int* u2) {
   *u2 = (int)((0x232121010ull >> (4 * q)) & 15);
 }
 
+// index of (pair type 1..6, nucleotide 1..4, nucleotide 1..4) in the compacted mismatch tables of PfHot
+ADP_HD int mm_index(int type, int a, int b) { return type * 16 + a * 4 + b - 21; }
+
 template <class E>
 ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
   for (int q = ex.tid(); q < 256; q += ex.nthreads()) {
@@ -118,7 +121,6 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
     const int x = (a >> 2) + 1, u = (a & 3) + 1, y = (b >> 2) + 1, v = (b & 3) + 1;
     const int t = pair_type(x, y);
     H->FI[q] = t ? T->mmI[t][u][v] : 0.;
-    H->F1n[q] = t ? T->mm1nI[t][u][v] : 0.;
     H->FM[q] = t ? T->mmM[rtype(t)][v][u] * (t > 2 ? T->TermAU : 1.) * T->MLintern : 0.;
     const double inv = t ? 1. / T->mmI[t][u][v] : 0.;
     H->RI[q] = inv;
@@ -131,9 +133,12 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
     H->tap1n[q] = (q >= 3 && q <= 29) ? T->interior[q + 1] * T->ninio[q - 1] * T->scale[q + 3] : 0.;
   }
   for (int q = ex.tid(); q < 200; q += ex.nthreads()) {
-    H->mm23[q] = (&T->mm23I[0][0][0])[q];
-    H->mmH[q] = (&T->mmH[0][0][0])[q];
-    H->mmExt[q] = (&T->mmExt[0][0][0])[q];
+    if (q < 96) {
+      const int t = q / 16 + 1, a = ((q >> 2) & 3) + 1, b = (q & 3) + 1;
+      H->mm23[q] = T->mm23I[t][a][b];
+      H->mmH[q] = T->mmH[t][a][b];
+      H->mmExt[q] = T->mmExt[t][a][b];
+    }
     if (q < 64) H->stack[q] = (&T->stack[0][0])[q];
     if (q < 40) { H->dangle5[q] = (&T->dangle5[0][0])[q]; H->dangle3[q] = (&T->dangle3[0][0])[q]; }
     if (q < 16) {
@@ -222,7 +227,7 @@ ADP_HD double fast_stem_ml(const SeqCtx& c, const PfHot& H, const FastWork& w, i
 }
 ADP_HD double fast_stem_ext(const SeqCtx& c, const PfHot& H, int type, int i, int j) {
   double e = 1.;
-  if (i > 1 && j < c.n) e = H.mmExt[(type * 5 + c.S[i - 1]) * 5 + c.S[j + 1]];
+  if (i > 1 && j < c.n) e = H.mmExt[mm_index(type, c.S[i - 1], c.S[j + 1])];
   else if (i > 1) e = H.dangle5[type * 5 + c.S[i - 1]];
   else if (j < c.n) e = H.dangle3[type * 5 + c.S[j + 1]];
   if (type > 2) e *= H.TermAU;
@@ -260,7 +265,7 @@ ADP_HD double fast_hairpin(const SeqCtx& c, const PfHot& H, const PfTables* G, c
   double q;
   if (sx >= 0) q = (u == 4 ? G->tetra_x : u == 6 ? G->hex_x : G->tri_x)[sx] * w.scaleG[u + 2];
   else if (u == 3) q = type > 2 ? w.hpw[3] * H.TermAU : w.hpw[3];
-  else q = w.hpw[u] * H.mmH[(type * 5 + c.S[i + 1]) * 5 + c.S[j - 1]];
+  else q = w.hpw[u] * H.mmH[mm_index(type, c.S[i + 1], c.S[j - 1])];
   if (is_motif_site(c, i, j)) q *= motif_boltz;   // the bound motif REPLACES the empty loop
   return q;
 }
@@ -277,7 +282,7 @@ ADP_HD const double* corner_entry(const PfHot& H, const PfTables* G, int q, int 
   else if (q == 5) p = &G->int21[type2][type][sq1][si1][sp1];
   else if (q == 6) p = &G->int22[type][type2][si1][sp1][sq1][sj1];
   else {
-    f *= H.mm23[(type * 5 + si1) * 5 + sj1] * H.mm23[(type2 * 5 + sq1) * 5 + sp1];
+    f *= H.mm23[mm_index(type, si1, sj1)] * H.mm23[mm_index(type2, sq1, sp1)];
     p = &H.one;
   }
   *fac = f;
@@ -654,7 +659,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
 #endif
           // ---- cell total
           other += cval * ctab;
-          acc = other + au_factor(H, si, sj) * accB + H.F1n[codeij] * acc1n + accML * (H.MLclosing * H.FM[codeij] * H.scale2);
+          acc = other + au_factor(H, si, sj) * accB + H.R1[codeij] * H.FI[codeij] * acc1n + accML * (H.MLclosing * H.FM[codeij] * H.scale2);
         }
         ADP_TICK(11)
         acc = ex.group_sum_rt(acc, Gs);
@@ -988,7 +993,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           }
           // ---- cell total
           other += cval * ctab;
-          val = other + au_factor(H, sk, sl) * accB + H.F1n[codekl] * acc1n;
+          val = other + au_factor(H, sk, sl) * accB + H.R1[codekl] * H.FI[codekl] * acc1n;
           if (k >= 2 && l < n) val += accML * (H.FM[codekl] * H.scale2);
         }
         ADP_TICK(11)
