@@ -209,6 +209,9 @@ ADP_HD bool run_mfe_job_fast(const E& ex, const MfeJob& job, void* small, int32_
   w.cp = cv.take<uint8_t>(w.ld);
   w.cells = cv.take<uint16_t>(w.ld);
   w.counter = cv.take<int>(4);
+  w.hpw = cv.take<int32_t>(w.ld);
+  w.spx = cv.take<int16_t>((size_t)3 * w.ld);
+  w.lvoff = cv.take<int>(32);
   MfeWork tb;                              // what the shared traceback needs besides the matrices
   tb.stack = cv.take<int16_t>((size_t)(4 * n + 16) * 3);
   tb.out = cv.take<char>(n + 16);
@@ -230,6 +233,7 @@ ADP_HD bool run_mfe_job_fast(const E& ex, const MfeJob& job, void* small, int32_
     codes.cp = w.cp;
     if (!fast_codes(ex, c, codes)) w.counter[2] = 1;
   }
+  mfe_special_hairpins(ex, c, job.T, w);
   ex.sync();
   if (w.counter[2]) return false;
 

@@ -23,17 +23,25 @@ struct MfeHot {                       // shared memory, staged once per job
   int32_t tapB[32];                   // bulge[u]                      (u >= 2)
   int32_t tap1n[32];                  // interior[u+1] + ninio[u-1]    (1 x u loop, u >= 3)
   int32_t ML_base, ML_closing, TermAU, inf;
+  // what hairpins, stems at the sequence ends, exterior stems and the corner candidates read (see PfHot): only int11 / int21 /
+  // int22 and the special-hairpin energies stay in global memory
+  int32_t stack[64];                  // [type][type2]
+  int32_t mm23[96], mmH[96], mmExt[96];       // compacted mismatch tables, see mm_index (pf_fast.cuh)
+  int32_t dangle5[40], dangle3[40];
+  int32_t cfe[16];                    // per corner candidate q: bulge[1] | interior[5] + ninio[1] | 0
+  int32_t zero, ML_intern, pad0, pad1;
 };
 
 struct FastConstI {
-  int32_t ip[32];                     // interior[s]
-  int32_t nin[32];                    // ninio(d)
+  int32_t ip[32];                     // [parity][q]: interior[s] of level s = 4 + parity + 2q (kInf beyond kMaxLoop)
+  int32_t nin[32];                    // [parity][q]: ninio(s - 4)
 };
 
 ADP_HD void fill_fast_const_i(FastConstI* fc, const IntTables* T) {
-  for (int q = 0; q < 32; q++) {
-    fc->ip[q] = q <= 30 ? T->interior[q] : kInf;
-    fc->nin[q] = q <= 30 ? T->ninio[q] : kInf;
+  for (int t = 0; t < 32; t++) {
+    const int s = 4 + (t >> 4) + 2 * (t & 15);
+    fc->ip[t] = s <= kMaxLoop ? T->interior[s] : kInf;
+    fc->nin[t] = s <= kMaxLoop ? T->ninio[s - 4] : kInf;
   }
 }
 
@@ -65,7 +73,19 @@ ADP_HD void stage_mfe_hot(const E& ex, MfeHot* H, const IntTables* T) {
     H->tapB[q] = (q >= 2 && q <= 30) ? T->bulge[q] : kInf;
     H->tap1n[q] = (q >= 3 && q <= 29) ? T->interior[q + 1] + T->ninio[q - 1] : kInf;
   }
-  if (ex.tid() == 0) { H->ML_base = T->ML_base; H->ML_closing = T->ML_closing; H->TermAU = T->TerminalAU; H->inf = kInf; }
+  for (int q = ex.tid(); q < 96; q += ex.nthreads()) {
+    const int t = q / 16 + 1, a = ((q >> 2) & 3) + 1, b = (q & 3) + 1;
+    H->mm23[q] = T->mm23I[t][a][b];
+    H->mmH[q] = T->mmH[t][a][b];
+    H->mmExt[q] = T->mmExt[t][a][b];
+    if (q < 64) H->stack[q] = (&T->stack[0][0])[q];
+    if (q < 40) { H->dangle5[q] = (&T->dangle5[0][0])[q]; H->dangle3[q] = (&T->dangle3[0][0])[q]; }
+    if (q < 16) H->cfe[q] = (q == 1 || q == 2) ? T->bulge[1] : (q == 7 || q == 8) ? T->interior[5] + T->ninio[1] : 0;
+  }
+  if (ex.tid() == 0) {
+    H->ML_base = T->ML_base; H->ML_closing = T->ML_closing; H->TermAU = T->TerminalAU; H->inf = kInf;
+    H->zero = 0; H->ML_intern = T->ML_intern; H->pad0 = 0; H->pad1 = 0;
+  }
 #if !defined(__CUDA_ARCH__)
   fill_fast_const_i(&h_fast_const_i, T);
 #endif
@@ -82,6 +102,9 @@ struct MfeFastWork {
   uint8_t* cp;
   uint16_t* cells;
   int* counter;
+  int32_t* hpw;    // [ld]: hairpin[u] by loop size
+  int16_t* spx;    // [3][ld]: index of the special hairpin (tri / tetra / hexa loop) closed at i, or -1
+  int* lvoff;      // [32]: byte offsets of the row candidates of the level recursion, [parity][level]
   int32_t* dstate; // see FastWork::dstate
   int ld, R;
 };
@@ -89,16 +112,83 @@ struct MfeFastWork {
 ADP_HD size_t mfe_fast_small_bytes(int n) {
   const size_t ld = (size_t)fast_ld(n);
   return sizeof(MfeHot) + 64 + ctx_bytes(n) + kMfeFastVectors * ld * sizeof(int32_t) + 2 * ld + 2 * ld + 64 + 16 * 12
-         + (size_t)(4 * n + 16) * 3 * sizeof(int16_t) + (n + 16) + 64;      // + traceback stack and output string
+         + (size_t)(4 * n + 16) * 3 * sizeof(int16_t) + (n + 16) + 64       // + traceback stack and output string
+         + ld * sizeof(int32_t) + 3 * ld * sizeof(int16_t) + 32 * sizeof(int) + 48;
 }
 ADP_HD size_t mfe_fast_matrix_ints(int n) { return 2 * t4_count(n) + 4; }
 
 ADP_HD int imin(int a, int b) { return a < b ? a : b; }
 ADP_HD int au_e(const MfeHot& H, int a, int b) { return a * b == 6 ? 0 : H.TermAU; }
 
-ADP_HD int mfe_stem_ml(const SeqCtx& c, const MfeHot& H, const IntTables& P, const MfeFastWork& w, int type, int i, int j) {
+// stems as stem_e (fold_common.cuh), from the staged tables
+ADP_HD int mfe_stem_ml(const SeqCtx& c, const MfeHot& H, const MfeFastWork& w, int type, int i, int j) {
   if (i > 1 && j < c.n) return H.FM[(w.cn[j] << 4) | w.cp[i]];
-  return stem_e(P, type, i > 1, c.S[i - 1], j < c.n, c.S[j + 1], false);
+  int e = 0;
+  if (i > 1) e = H.dangle5[type * 5 + c.S[i - 1]];
+  else if (j < c.n) e = H.dangle3[type * 5 + c.S[j + 1]];
+  if (type > 2) e += H.TermAU;
+  return e + H.ML_intern;
+}
+ADP_HD int mfe_stem_ext(const SeqCtx& c, const MfeHot& H, int type, int i, int j) {
+  int e = 0;
+  if (i > 1 && j < c.n) e = H.mmExt[mm_index(type, c.S[i - 1], c.S[j + 1])];
+  else if (i > 1) e = H.dangle5[type * 5 + c.S[i - 1]];
+  else if (j < c.n) e = H.dangle3[type * 5 + c.S[j + 1]];
+  if (type > 2) e += H.TermAU;
+  return e;
+}
+
+// special hairpins of the job and the hairpin energies by size, found / copied once per job
+template <class E>
+ADP_HD void mfe_special_hairpins(const E& ex, const SeqCtx& c, const IntTables* P, MfeFastWork& w) {
+  const int n = c.n, ld = w.ld;
+  for (int t = ex.tid(); t < 3 * ld; t += ex.nthreads()) {
+    const int cls = t / ld, i = t - cls * ld;
+    const int u = cls == 0 ? 3 : cls == 1 ? 4 : 6;
+    int idx = -1;
+    uint32_t code;
+    if (i >= 1 && i + u + 1 <= n && pack_window(c.S, i, u + 2, &code)) {
+      const uint32_t* codes = u == 4 ? P->tetra_code : u == 6 ? P->hex_code : P->tri_code;
+      const int cnt = u == 4 ? P->n_tetra : u == 6 ? P->n_hex : P->n_tri;
+      for (int k = 0; k < cnt; k++)
+        if (codes[k] == code) { idx = k; break; }
+    }
+    w.spx[t] = (int16_t)idx;
+  }
+  for (int u = ex.tid(); u < ld; u += ex.nthreads()) w.hpw[u] = P->hairpin[u];
+}
+
+// hairpin_cell_e (mfe_core.cuh) from the staged tables
+ADP_HD int mfe_fast_hairpin(const SeqCtx& c, const MfeHot& H, const IntTables& P, const MfeFastWork& w, int motif_dcal, int i, int j, int type) {
+  const int u = j - i - 1;
+  if ((int)c.upr[i + 1] < u) return kInf;
+  int sx = -1;
+  if (u == 3) sx = w.spx[i];
+  else if (u == 4) sx = w.spx[w.ld + i];
+  else if (u == 6) sx = w.spx[2 * w.ld + i];
+  int e;
+  if (sx >= 0) e = (u == 4 ? P.tetra_e : u == 6 ? P.hex_e : P.tri_e)[sx];
+  else if (u == 3) e = w.hpw[3] + (type > 2 ? H.TermAU : 0);
+  else e = w.hpw[u] + H.mmH[mm_index(type, c.S[i + 1], c.S[j - 1])];
+  if (is_motif_site(c, i, j)) e += motif_dcal;
+  return e;
+}
+
+// Corner candidate q (see corner_entry in pf_fast.cuh): the energy is  *add + (*returned address); same cases as interior_e.
+ADP_HD const int32_t* mfe_corner_entry(const MfeHot& H, const IntTables& P, int q, int type, int type2, int si1, int sj1, int sp1, int sq1, int* add) {
+  int a = H.cfe[q];
+  const int32_t* p;
+  if (q <= 2) p = &H.stack[type * 8 + type2];
+  else if (q == 3) p = &P.int11[type][type2][si1][sj1];
+  else if (q == 4) p = &P.int21[type][type2][si1][sq1][sj1];
+  else if (q == 5) p = &P.int21[type2][type][sq1][si1][sp1];
+  else if (q == 6) p = &P.int22[type][type2][si1][sp1][sq1][sj1];
+  else {
+    a += H.mm23[mm_index(type, si1, sj1)] + H.mm23[mm_index(type2, sq1, sp1)];
+    p = &H.zero;
+  }
+  *add = a;
+  return p;
 }
 
 // matrix view for the traceback: plain C(i,j), F(i,j), kInf where the trimmed triangles have no cell
@@ -118,26 +208,23 @@ struct FastMfeView {
   ADP_HD int f(int i, int j) const { return j - i < 4 ? kInf : F[t4(i, j)]; }
 };
 
-// One level of the (min,+) recursion; see ADP_LEVEL_STEP in pf_fast.cuh.  `zp` points at an always-kInf word.
-#define ADP_MLEVEL_STEP(PAR, Q, P1, C1, P2, C2)                                        \
-  if (4 + (PAR) + 2 * (Q) <= kMaxLoop) {                                              \
-    constexpr int S = 4 + (PAR) + 2 * (Q);                                            \
-    const bool on = S <= smax;                                                        \
-    const int32_t* p1 = (on && (C1)) ? (P1) : zp;                                     \
-    const int32_t* p2 = (S > 4 && on && (C2)) ? (P2) : zp;                            \
-    int v = imin(ADP_FCI.nin[S - 4 > 0 ? S - 4 : 0] + imin(*p1, *p2), kInf);          \
-    if ((Q) > 0) v = imin(v, (on && g) ? d[(Q) > 0 ? (Q) - 1 : 0] : kInf);            \
-    if (S >= 6) gen = imin(gen, ADP_FCI.ip[S] + v);                                   \
+// One level of the (min,+) recursion; see ADP_LEVEL_STEP in pf_fast.cuh (run-time level parity, one code path).  `zp` points at
+// an always-kInf word.
+#define ADP_MLEVEL_STEP(Q, ADDR1, C1, ADDR2, C2)                                       \
+  {                                                                                   \
+    const int32_t* p1 = (4 + 2 * (Q) <= sm1 && C1(Q)) ? ADDR1(Q) : zp;                \
+    const int32_t* p2 = (4 + 2 * (Q) <= sm2 && ((Q) > 0 || par != 0) && C2(Q)) ? ADDR2(Q) : zp; \
+    int v = imin(fcn[Q] + imin(*p1, *p2), kInf);                                      \
+    if ((Q) > 0) v = imin(v, (!kCst || (4 + 2 * (Q) <= sm && g)) ? d[(Q) > 0 ? (Q) - 1 : 0] : kInf); \
+    if ((Q) > 0) gen = imin(gen, fci[Q] + v);                                         \
     d[Q] = v;                                                                         \
   }
-#define ADP_MLEVEL_PASS(PAR, B1, C1, B2, C2)                                                        \
-  ADP_MLEVEL_STEP(PAR, 13, B1, C1, B2, C2) ADP_MLEVEL_STEP(PAR, 12, B1, C1, B2, C2)                \
-  ADP_MLEVEL_STEP(PAR, 11, B1, C1, B2, C2) ADP_MLEVEL_STEP(PAR, 10, B1, C1, B2, C2)                \
-  ADP_MLEVEL_STEP(PAR, 9, B1, C1, B2, C2) ADP_MLEVEL_STEP(PAR, 8, B1, C1, B2, C2)                  \
-  ADP_MLEVEL_STEP(PAR, 7, B1, C1, B2, C2) ADP_MLEVEL_STEP(PAR, 6, B1, C1, B2, C2)                  \
-  ADP_MLEVEL_STEP(PAR, 5, B1, C1, B2, C2) ADP_MLEVEL_STEP(PAR, 4, B1, C1, B2, C2)                  \
-  ADP_MLEVEL_STEP(PAR, 3, B1, C1, B2, C2) ADP_MLEVEL_STEP(PAR, 2, B1, C1, B2, C2)                  \
-  ADP_MLEVEL_STEP(PAR, 1, B1, C1, B2, C2) ADP_MLEVEL_STEP(PAR, 0, B1, C1, B2, C2)
+#define ADP_MLEVEL_PASS(A1, C1, A2, C2)                                                \
+  ADP_MLEVEL_STEP(13, A1, C1, A2, C2) ADP_MLEVEL_STEP(12, A1, C1, A2, C2) ADP_MLEVEL_STEP(11, A1, C1, A2, C2) \
+  ADP_MLEVEL_STEP(10, A1, C1, A2, C2) ADP_MLEVEL_STEP(9, A1, C1, A2, C2) ADP_MLEVEL_STEP(8, A1, C1, A2, C2)  \
+  ADP_MLEVEL_STEP(7, A1, C1, A2, C2) ADP_MLEVEL_STEP(6, A1, C1, A2, C2) ADP_MLEVEL_STEP(5, A1, C1, A2, C2)  \
+  ADP_MLEVEL_STEP(4, A1, C1, A2, C2) ADP_MLEVEL_STEP(3, A1, C1, A2, C2) ADP_MLEVEL_STEP(2, A1, C1, A2, C2)  \
+  ADP_MLEVEL_STEP(1, A1, C1, A2, C2) ADP_MLEVEL_STEP(0, A1, C1, A2, C2)
 #define ADP_MLEVEL_INF() \
   d[0] = d[1] = d[2] = d[3] = d[4] = d[5] = d[6] = d[7] = d[8] = d[9] = d[10] = d[11] = d[12] = d[13] = kInf;
 
@@ -189,6 +276,7 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
   if (mem_state)
     for (int k = tid; k < 2 * R * kFastLevels; k += nt) w.dstate[k] = kInf;
   if (tid == 0) { w.counter[0] = 0; w.counter[1] = 0; }
+  for (int t = tid; t < 32; t += nt) w.lvoff[t] = 0;
   ex.sync();
   const int mlb = H.ML_base;
   if (tid == 0) {
@@ -214,23 +302,29 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
       if (key < jn + 1) key += R;
       const int i = key - jn;
       if (i >= 1 && i <= nr) {
-        int smax = jn - i - 6;
-        if (smax > kMaxLoop) smax = kMaxLoop;
+        int sm = jn - i - 6;
+        if (sm > kMaxLoop) sm = kMaxLoop;
+        sm -= par;                                     // level Q is on iff 4 + 2Q <= sm
         int gen = kInf;
-        if (smax >= 4) {
+        if (sm + par >= 4) {
           const int upr_i1 = kCst ? (int)c.upr[i + 1] : 1000;
           const bool g = upr_i1 >= 1 && cuj1;
           const bool ok1 = upr_i1 >= 2, ok2 = upl_j1 >= 2;
-          const int32_t* xi = col3 + i;
-          const int32_t* qrow = C + i + 2;
-#define ADP_P1 (qrow + (((jn - 3 - S) * (jn - 4 - S)) >> 1))
-#define ADP_C1 (!kCst || (ok1 && upl_j1 >= S - 2))
-#define ADP_P2 (xi + S)
-#define ADP_C2 (!kCst || (ok2 && upr_i1 >= S - 2))
-          if (par) { ADP_MLEVEL_PASS(1, ADP_P1, ADP_C1, ADP_P2, ADP_C2) } else { ADP_MLEVEL_PASS(0, ADP_P1, ADP_C1, ADP_P2, ADP_C2) }
-#undef ADP_P1
+          const int sm1 = sm, sm2 = sm;
+          const int lim1 = upl_j1 - par - 2, lim2 = upr_i1 - par - 2;
+          const int32_t* xi = col3 + i + par + 4;      // C+FI(i+S-1, jn-3) = xi[2Q]
+          const char* qrow = reinterpret_cast<const char*>(C + i + 2);    // C+FI(i+3, l), l = jn+1-S: offset from the table
+          const int32_t* fcn = ADP_FCI.nin + (par << 4);
+          const int32_t* fci = ADP_FCI.ip + (par << 4);
+          ADP_LEVEL_OFFSETS(w.lvoff + (par << 4))
+#define ADP_A1(Q) reinterpret_cast<const int32_t*>(qrow + lo[Q])
+#define ADP_C1(Q) (!kCst || (ok1 && 2 * (Q) <= lim1))
+#define ADP_A2(Q) (xi + 2 * (Q))
+#define ADP_C2(Q) (!kCst || (ok2 && 2 * (Q) <= lim2))
+          ADP_MLEVEL_PASS(ADP_A1, ADP_C1, ADP_A2, ADP_C2)
+#undef ADP_A1
 #undef ADP_C1
-#undef ADP_P2
+#undef ADP_A2
 #undef ADP_C2
         } else {
           ADP_MLEVEL_INF()
@@ -257,6 +351,13 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
     // ---- interval 1: C(i,j) for the listed cells
     {
       if (tid == 0) w.counter[(j + 1) & 1] = 0;
+      ADP_NOUNROLL
+      for (int t = tid; t < 32; t += nt) {
+        // byte offsets of the row candidates of the level recursion of column j+1: level S reads C+FI(i+3, j+2-S)
+        const int S = 4 + (t >> 4) + 2 * (t & 15);
+        const int l = j + 2 - S;
+        w.lvoff[t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(int32_t);
+      }
       const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const int32_t* x1n_rd = w.vecp(4 + (j & 1));     // column j-2
@@ -277,49 +378,55 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
           if (u1cap > kMaxLoop) u1cap = kMaxLoop;
           if (u2cap > kMaxLoop) u2cap = kMaxLoop;
           int other = kInf, accB = kInf, acc1n = kInf, accML = kInf;
+          int cadd = kInf, ctab = 0;
           if (sub == 0) {
-            other = hairpin_cell_e(P, c, motif_dcal, i, j, type);
+            other = mfe_fast_hairpin(c, H, P, w, motif_dcal, i, j, type);
             other = imin(other, H.FI[codeij] + imin(gen0[i], gen1[i]));
           }
           if (room >= 0) {
+            // corner candidates, software-pipelined and rolled like in pf_fast.cuh: the table load of a round is consumed in the next
+            ADP_NOUNROLL
             for (int q = sub; q < 9; q += Gs) {
               int u1, u2;
               corner_u(q, &u1, &u2);
+              int a2 = kInf;
+              const int32_t* p2 = &H.zero;
               if (u1 <= u1cap && u2 <= u2cap && u1 + u2 <= room) {
                 const int k = i + 1 + u1, l = j - 1 - u2;
                 const int v = C[t4(k, l)];
-                if (v < kInfHalf)
-                  other = imin(other, v + H.RI[(cn[l] << 4) | cp[k]] +
-                                          interior_e(P, u1, u2, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1]));
+                if (v < kInfHalf) {
+                  int add;
+                  p2 = mfe_corner_entry(H, P, q, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1], &add);
+                  a2 = v + H.RI[(cn[l] << 4) | cp[k]] + add;
+                }
               }
+              const int t2 = *p2;
+              other = imin(other, cadd + ctab);
+              cadd = a2;
+              ctab = t2;
             }
+            // the four 1-D filters along the loop's axes fused into one loop (see pf_fast.cuh)
             {
-              const int hi = room < u2cap ? room : u2cap;
-              const int cpk = cp[i + 1];
-              for (int u2 = 2 + sub; u2 <= hi; u2 += Gs) {
-                const int l = j - 1 - u2;
-                accB = imin(accB, C[t4(i + 1, l)] + H.RB[(cn[l] << 4) | cpk] + H.tapB[u2]);
-              }
-            }
-            if (u1cap >= 1) {
-              int hi = room - 1 < u2cap ? room - 1 : u2cap;
-              if (hi > kMaxLoop - 1) hi = kMaxLoop - 1;
-              const int cpk = cp[i + 2];
-              for (int u2 = 3 + sub; u2 <= hi; u2 += Gs) {
-                const int l = j - 1 - u2;
-                acc1n = imin(acc1n, C[t4(i + 2, l)] + H.R1[(cn[l] << 4) | cpk] + H.tap1n[u2]);
-              }
-            }
-            {
-              const int hi = room < u1cap ? room : u1cap;
+              const int hiB3 = room < u2cap ? room : u2cap;
+              const int hiB5 = room < u1cap ? room : u1cap;
+              int hi13 = room - 1 < u2cap ? room - 1 : u2cap, hi31 = room - 1 < u1cap ? room - 1 : u1cap;
+              if (hi13 > kMaxLoop - 1) hi13 = kMaxLoop - 1;
+              if (hi31 > kMaxLoop - 1) hi31 = kMaxLoop - 1;
+              if (u1cap < 1) hi13 = -1;
+              if (u2cap < 1) hi31 = -1;
+              const int hmax = hiB3 > hiB5 ? hiB3 : hiB5;
+              const int cpk1 = cp[i + 1], cpk2 = cp[i + 2];
               const int32_t* xa = xA + i + 1;
-              for (int u1 = 2 + sub; u1 <= hi; u1 += Gs) accB = imin(accB, xa[u1] + H.tapB[u1]);
-            }
-            if (u2cap >= 1) {
-              int hi = room - 1 < u1cap ? room - 1 : u1cap;
-              if (hi > kMaxLoop - 1) hi = kMaxLoop - 1;
               const int32_t* xn = x1n_rd + i + 1;
-              for (int u1 = 3 + sub; u1 <= hi; u1 += Gs) acc1n = imin(acc1n, xn[u1] + H.tap1n[u1]);
+              for (int u = 2 + sub; u <= hmax; u += Gs) {
+                const int l = j - 1 - u;
+                const int cl = cn[l] << 4;
+                const int32_t* pb = C + t4(i + 1, l);
+                const int b3 = pb[0] + H.RB[cl | cpk1], n3 = pb[1] + H.R1[cl | cpk2];
+                const int b5 = xa[u], n5 = xn[u];
+                accB = imin(accB, H.tapB[u] + imin(u <= hiB3 ? b3 : kInf, u <= hiB5 ? b5 : kInf));
+                acc1n = imin(acc1n, H.tap1n[u] + imin(u <= hi13 ? n3 : kInf, u <= hi31 ? n5 : kInf));
+              }
             }
           }
           {
@@ -333,6 +440,7 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
               step += step2;
             }
           }
+          other = imin(other, cadd + ctab);
           best = imin(imin(other, au_e(H, si, sj) + accB), imin(H.F1n[codeij] + acc1n, accML + H.ML_closing + H.FM[codeij]));
         }
         best = ex.group_min_rt(best, Gs);
@@ -341,8 +449,8 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
           C[t4(i, j)] = (best < kInf && i > 1 && j < n) ? best + H.FI[(cn[j] << 4) | cp[i]] : best;     // stored premultiplied
           int e = kInf;
           if (best < kInf) {
-            fm1_cur[i] = imin(fm1_cur[i], best + mfe_stem_ml(c, H, P, w, type, i, j));
-            if (f5[i - 1] < kInfHalf) e = f5[i - 1] + best + stem_e_at(P, c, type, i, j, true);
+            fm1_cur[i] = imin(fm1_cur[i], best + mfe_stem_ml(c, H, w, type, i, j));
+            if (f5[i - 1] < kInfHalf) e = f5[i - 1] + best + mfe_stem_ext(c, H, type, i, j);
           }
           ext[slot] = e;
         }
