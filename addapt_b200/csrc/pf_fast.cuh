@@ -78,6 +78,9 @@ struct PfHot {                        // shared memory, staged once per CTA
   double dangle5[40], dangle3[40];
   double cfac[16];                    // per corner candidate q: scale[u1+u2+2] * (bulge[1] | interior[5] * ninio[1] | 1)
   double one, MLintern;
+  uint8_t tyr[256];                   // by position codes (nucleotide + 3' neighbour, nucleotide + 5' neighbour): pair type of the
+                                      // two NEIGHBOURS, 3' one first -- the reversed type of the stacked inner pair (inside), the type
+                                      // of the stacked enclosing pair (outside)
 };
 
 // size-indexed factors of the generic interior loops; read with compile-time indices
@@ -127,6 +130,7 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
     H->RB[q] = t ? (t > 2 ? T->TermAU : 1.) * inv : 0.;
     H->R1[q] = t ? T->mm1nI[t][u][v] * inv : 0.;
     H->RM[q] = t ? H->FM[q] * inv : 0.;
+    H->tyr[q] = (uint8_t)pair_type(v, u);
   }
   for (int q = ex.tid(); q < 32; q += ex.nthreads()) {
     H->tapB[q] = (q >= 2 && q <= 30) ? T->bulge[q] * T->scale[q + 2] : 0.;
@@ -589,8 +593,13 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
             // corner candidates through the full tables, one per lane and round.  Software-pipelined and kept rolled (code size):
             // the table load of a round is issued in that round and consumed in the next, the last one after the filters below.
 #if !defined(ADP_X_NOCORNER)
+            if (sub == Gs - 1) {
+              // the stack (u1 = u2 = 0) as straight-line code on the group's last lane: both types come from the cell's own codes
+              const double v = qb[t4(i + 1, j - 1)] * H.RI[(cn[j - 1] << 4) | cp[i + 1]];
+              other += v * H.cfac[0] * H.stack[type * 8 + H.tyr[codeij]];
+            }
             ADP_NOUNROLL
-            for (int q = sub; q < 9; q += Gs) {
+            for (int q = 1 + sub; q < 9; q += Gs) {
               int u1, u2;
               corner_u(q, &u1, &u2);
               double v2 = 0.;
@@ -928,8 +937,13 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           if (k >= 2 && l < n) {
             const int t2r = rtype(type);
 #if !defined(ADP_X_OUT_NOCORNER)
+            if (sub == Gs - 1) {
+              // the enclosing stack (i,j) = (k-1,l+1) as straight-line code on the group's last lane
+              const double v = qb[t4(k - 1, l + 1)] * H.RI[(cn[k - 1] << 4) | cp[l + 1]];
+              other += v * H.cfac[0] * H.stack[H.tyr[codekl] * 8 + t2r];
+            }
             ADP_NOUNROLL
-            for (int q = sub; q < 9; q += Gs) {       // software-pipelined like the inside pass
+            for (int q = 1 + sub; q < 9; q += Gs) {       // software-pipelined like the inside pass
               int u1, u2;
               corner_u(q, &u1, &u2);
               double v2 = 0.;
