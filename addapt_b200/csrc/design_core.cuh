@@ -87,7 +87,7 @@ ADP_HD double thermostat_T(int kind, const double* args, int step) {
 }
 
 // Shared-memory bytes a design CTA needs besides the fold working set.
-ADP_HD size_t design_extra_bytes(int n_max) { return 96 + (size_t)(n_max + 16) * 4 + (kMaxVariants + kMaxTerms * kMaxCtx + 8 + kMaxTrain) * sizeof(double); }
+ADP_HD size_t design_extra_bytes(int n_max) { return 96 + (size_t)(n_max + 16) * 4 + (kMaxVariants + kMaxTerms * kMaxCtx + 8) * sizeof(double); }
 
 struct DesignScratch {
   uint8_t* full;     // contextual sequence  [n_max+16]
@@ -97,7 +97,8 @@ struct DesignScratch {
   double* dg;        // [kMaxVariants]
   double* terms;     // [kMaxCtx*kMaxTerms]
   double* bcast;     // [8] broadcast slots
-  double* train;     // [kMaxTrain] score differences the auto-scaling thermostat is trained on
+  double* train;     // [kMaxTrain] score differences the auto-scaling thermostat is trained on: the trajectory's slice of the
+                     // device-memory window that is carried from launch to launch (NULL for the other thermostats); touched once a step
 };
 
 ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
@@ -108,7 +109,7 @@ ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
   d.dg = cv.take<double>(kMaxVariants);
   d.terms = cv.take<double>(kMaxCtx * kMaxTerms);
   d.bcast = cv.take<double>(8);
-  d.train = cv.take<double>(kMaxTrain);
+  d.train = nullptr;      // set by the caller (not in shared memory: 4 KB that the fold working set needs)
 }
 
 // Score of the raw sequence `raw` (n ASCII bytes, readable by every thread).  Collective; every thread gets

@@ -65,15 +65,14 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
     if (a.step0 == 0) {
       for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.init_seq[p];
     } else {
-      // resume: sequences, scalar state and (auto-scaling thermostat) the partly filled training window
+      // resume: sequences and scalar state
       for (int p = threadIdx.x; p < n; p += blockDim.x) {
         s.d.cur[p] = a.final_seq[(size_t)t * n + p];
         s.d.best[p] = a.best_seq[(size_t)t * n + p];
       }
       if (threadIdx.x == 0) st = a.state[t];
-      if (a.train_state)
-        for (int q = threadIdx.x; q < a.state[t].ntrain; q += blockDim.x) s.d.train[q] = a.train_state[(size_t)t * a.train_stride + q];
     }
+    s.d.train = a.train_state ? a.train_state + (size_t)t * a.train_stride : nullptr;     // the training window stays in device memory
     __syncthreads();
     mc_trajectory<kFast>(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.step0, a.step1, a.thermo_kind, a.thermo_args, s.d, s.fold_small,
                          s.mats, &st, s.dstate);
@@ -82,8 +81,6 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
       a.final_seq[(size_t)t * n + p] = s.d.cur[p];
       a.best_seq[(size_t)t * n + p] = s.d.best[p];
     }
-    if (a.train_state)
-      for (int q = threadIdx.x; q < st.ntrain; q += blockDim.x) a.train_state[(size_t)t * a.train_stride + q] = s.d.train[q];
     if (threadIdx.x == 0) {
       a.state[t] = st;
       if (a.final_score) a.final_score[t] = st.cur_score;

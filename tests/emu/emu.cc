@@ -185,6 +185,8 @@ int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, 
     Carver cv(extra.data());
     DesignScratch d;
     carve_design(cv, d, nm);
+    std::vector<double> train(kMaxTrain);
+    d.train = train.data();
     SerialExec ex;
     std::memcpy(d.cur, pr->init_seq, pr->n);
     McState res;
