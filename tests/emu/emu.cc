@@ -207,4 +207,14 @@ int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, 
   } catch (std::string& er) { g_err = er; return -1; }
 }
 
+// Shared-memory footprint of one construct, as the launch planners size it (fold_kernels.cu plan_pf_fast / plan_mfe_fast,
+// design_kernels.cu plan_design): kind 0 = fast PF fold, 1 = fast PF fold inside the score / Monte-Carlo kernels, 2 = fast MFE.
+// tests/test_emu_parity.py keeps the benchmarked lengths at two (PF) / four (MFE) constructs per SM.
+size_t emu_smem_bytes(int kind, int n) {
+  if (kind == 2) return ((mfe_fast_small_bytes(n) + 15) & ~(size_t)15) + mfe_fast_matrix_ints(n) * sizeof(int32_t);
+  const size_t small = (fast_small_bytes(n) + 15) & ~(size_t)15;
+  const size_t mats = fast_matrix_doubles(n) * sizeof(double);
+  return kind == 1 ? small + design_extra_bytes(n) + 64 + mats : small + mats;
+}
+
 }  // extern "C"

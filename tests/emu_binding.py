@@ -36,6 +36,12 @@ class Emu:
             raise RuntimeError(L.emu_error().decode())
         self.kT = L.emu_kT(self.model)
 
+    def smem_bytes(self, kind, n):
+        """shared memory per construct as the launch planners size it: kind 0 fast PF, 1 fast PF in the design kernels, 2 fast MFE"""
+        self.lib.emu_smem_bytes.restype = C.c_size_t
+        self.lib.emu_smem_bytes.argtypes = [C.c_int, C.c_int]
+        return int(self.lib.emu_smem_bytes(kind, n))
+
     def _err(self):
         return ValueError(self.lib.emu_error().decode())
 

@@ -158,3 +158,13 @@ def test_move_table_errors(emu):
     bad = Problem("Nn", {"m": "()"}, [("m", "apo", True, 1.0)])       # partner not mutable: tests/test_sampling.cc:101-103
     with pytest.raises(ValueError):
         emu.mc_run(bad, 0, 0, 1)
+
+
+def test_shared_memory_budget(emu):
+    """Occupancy guard: a B200 SM has 228 KB of shared memory, 1 KB of it reserved per resident CTA.  The benchmarked constructs
+    must keep two (PF: 100-nt folds, the 102-nt rhf(6) design problem inside the score / Monte-Carlo kernels) and four (MFE, 100 nt)
+    constructs per SM -- losing one halves the occupancy (measured: -22 % on the design run)."""
+    per_sm = 228 * 1024
+    assert emu.smem_bytes(0, 100) <= per_sm // 2 - 1024
+    assert emu.smem_bytes(1, 102) <= per_sm // 2 - 1024
+    assert emu.smem_bytes(2, 100) <= per_sm // 4 - 1024
