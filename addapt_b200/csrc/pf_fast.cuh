@@ -13,22 +13,30 @@
 //    i.e. 27 updates per cell instead of 372 multiply-adds.  (i,j) -> (i+1,j-1) keeps i+j, so a thread that owns
 //    the anti-diagonal i+j keeps its 14 level sums IN REGISTERS while the column sweep walks along it: the
 //    recursion costs no shared memory and no barrier.  The outside pass runs the mirrored recursion over the
-//    enclosing pairs, (k,l) -> (k-1,l+1).  Level parity is a compile-time constant of the code path, so the loop
-//    size s is an immediate and the size-dependent factors come from the constant bank.
+//    enclosing pairs, (k,l) -> (k-1,l+1).  Level parity is a run-time, warp-uniform value: both parities share ONE code
+//    path (code size, see below), the size-dependent factors come from [parity][level] tables in the constant bank and the
+//    row offsets of a column from a 32-entry table in shared memory.
 //    Levels that are off for a thread (no room, or closed by the hard constraint) read an always-zero word instead, so
 //    the recursion is branch-free and every lane of a warp executes the same instructions.
 //  * Qb (and, in the outside pass, the outside weight) is stored PREMULTIPLIED by the generic mismatch factor of its
 //    pair, so the two border candidates of every level are single loads; the other readers multiply by a ratio from a
 //    16x16 table (1/FI, terminal-AU/FI, F1n/FI, FM/FI).
 //  * The candidates on the loop's axes (bulges, 1xn loops: 112 per cell) are four 1-D filters; the two that run
-//    down a column read a per-column vector premultiplied once, the two that run along a row are evaluated by the
-//    cell's lanes.  The 9 corner candidates (stack, bulge-1, 1x1, 1x2, 2x2, 2x3) use the full tables.
+//    down a column read a per-column vector premultiplied once, the two that run along a row read the matrix; all four
+//    are evaluated in ONE loop per lane so that their load chains overlap.  The 9 corner candidates (stack, bulge-1,
+//    1x1, 1x2, 2x2, 2x3) use the full tables: the stack as straight-line code, the other eight in a rolled loop whose
+//    table load is issued one round ahead of its use.
 //  * All per-pair factors come from 16x16 tables indexed by two one-byte position codes
-//    (nucleotide + 3' neighbour, nucleotide + 5' neighbour), staged once per job.
+//    (nucleotide + 3' neighbour, nucleotide + 5' neighbour), staged once per job -- together with every other small
+//    table a cell reads (stack, hairpin / exterior / 2x3 mismatches, dangles, hairpin weights by size, the special
+//    hairpin closed at each position): only int11 / int21 / int22 are read from global memory inside the sweep.
 //  * Only cells that can pair are evaluated: each column compacts them into a list, and a power-of-two lane group
 //    per cell (sized so the list fills the CTA) splits the cell's terms and reduces with shuffles.
-//  * Two barriers per column: the sparse per-cell phase alone, then everything that is independent of it (Qm of
-//    the column, the level recursion / carriers / compaction of the NEXT column) in one interval.
+//  * Two barriers per column: the sparse per-cell phase alone, then everything that is independent of it (the level
+//    recursion / carriers / compaction / per-row hairpin and stem factors of the NEXT column, and Qm of the PREVIOUS
+//    column from a queue of warp-sized chunks that evens out the warps) in one interval.
+//  * The code is kept small on purpose: the SM's instruction caches hold 6 KB (L0) and 32 KB (L1.5), the two resident
+//    CTAs are usually in different passes, and the kernel's speed follows its SASS size.
 #pragma once
 #include "fold_common.cuh"
 
