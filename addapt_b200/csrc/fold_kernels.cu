@@ -3,6 +3,8 @@
 // batch layout.  No tensor cores (the recursions are not dense contractions), no library calls.
 #include <cstdlib>
 
+#include <vector>
+
 #include "fold_jobs.cuh"
 #include "kernels.h"
 
@@ -281,9 +283,31 @@ LaunchPlan plan_pf_fast(const DeviceInfo& d, int n, int jobs) {
   return p;
 }
 
+#if defined(ADP_CORNER_TABLE)
+// experiment (pf_fast.cuh, build_corner_table): the table of the current device, built and uploaded on first use
+const double* device_corner_table(const PfTables* host_tables) {
+  static double* tables[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!tables[dev]) {
+    std::vector<double> h(kCornerEntries);
+    build_corner_table(host_tables, h.data());
+    double* d = nullptr;
+    if (cudaMalloc(&d, kCornerEntries * sizeof(double)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), kCornerEntries * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    tables[dev] = d;
+  }
+  return tables[dev];
+}
+#endif
+
 cudaError_t launch_pf_fast(const PfBatchArgs& a, const LaunchPlan& p, const PfTables* host_tables, cudaStream_t stream) {
   FastConst fc;
   fill_fast_const(&fc, host_tables);
+#if defined(ADP_CORNER_TABLE)
+  fc.corner = device_corner_table(host_tables);
+  if (!fc.corner) return cudaErrorMemoryAllocation;
+#endif
   cudaError_t ce = cudaMemcpyToSymbolAsync(c_fast_const, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
   if (ce != cudaSuccess) return ce;
   if (p.threads == 256) {
@@ -316,9 +340,30 @@ LaunchPlan plan_mfe_fast(const DeviceInfo& d, int n, int jobs) {
   return p;
 }
 
+#if defined(ADP_CORNER_TABLE)
+static const int32_t* device_corner_table_i(const IntTables* host_tables) {
+  static int32_t* tables[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!tables[dev]) {
+    std::vector<int32_t> h(kCornerEntriesI);
+    build_corner_table_i(host_tables, h.data());
+    int32_t* d = nullptr;
+    if (cudaMalloc(&d, kCornerEntriesI * sizeof(int32_t)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), kCornerEntriesI * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    tables[dev] = d;
+  }
+  return tables[dev];
+}
+#endif
+
 cudaError_t launch_mfe_fast(const MfeBatchArgs& a, const LaunchPlan& p, const IntTables* host_tables, cudaStream_t stream) {
   FastConstI fc;
   fill_fast_const_i(&fc, host_tables);
+#if defined(ADP_CORNER_TABLE)
+  fc.corner = device_corner_table_i(host_tables);
+  if (!fc.corner) return cudaErrorMemoryAllocation;
+#endif
   cudaError_t ce = cudaMemcpyToSymbolAsync(c_fast_const_i, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
   if (ce != cudaSuccess) return ce;
   if (p.threads == 256) {

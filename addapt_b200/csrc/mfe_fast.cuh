@@ -35,7 +35,30 @@ struct MfeHot {                       // shared memory, staged once per job
 struct FastConstI {
   int32_t ip[32];                     // [parity][q]: interior[s] of level s = 4 + parity + 2q (kInf beyond kMaxLoop)
   int32_t nin[32];                    // [parity][q]: ninio(s - 4)
+#if defined(ADP_CORNER_TABLE)
+  const int32_t* corner;              // experiment, see build_corner_table in pf_fast.cuh: [q-1][closing code][inner code] energies
+#endif
 };
+
+#if defined(ADP_CORNER_TABLE)
+constexpr size_t kCornerEntriesI = (size_t)9 << 16;      // all nine candidates (the MFE loop keeps the stack in the loop)
+inline void build_corner_table_i(const IntTables* T, int32_t* out) {
+  for (int q = 0; q < 9; q++) {
+    const int u1 = (int)((0x322211100ull >> (4 * q)) & 15), u2 = (int)((0x232121010ull >> (4 * q)) & 15);
+    for (int co = 0; co < 256; co++) {
+      const int a = co >> 4, b = co & 15;
+      const int si = (a >> 2) + 1, si1 = (a & 3) + 1, sj = (b >> 2) + 1, sj1 = (b & 3) + 1;
+      const int type = pair_type(si, sj);
+      for (int ci = 0; ci < 256; ci++) {
+        const int a2 = ci >> 4, b2 = ci & 15;      // cn[l], cp[k]
+        const int sl = (a2 >> 2) + 1, sl1 = (a2 & 3) + 1, sk = (b2 >> 2) + 1, sk1 = (b2 & 3) + 1;
+        const int t2 = pair_type(sk, sl);
+        out[((size_t)q << 16) | ((size_t)co << 8) | ci] = (type && t2) ? interior_e(*T, u1, u2, type, rtype(t2), si1, sj1, sk1, sl1) : 10000000;
+      }
+    }
+  }
+}
+#endif
 
 ADP_HD void fill_fast_const_i(FastConstI* fc, const IntTables* T) {
   for (int t = 0; t < 32; t++) {
@@ -88,6 +111,18 @@ ADP_HD void stage_mfe_hot(const E& ex, MfeHot* H, const IntTables* T) {
   }
 #if !defined(__CUDA_ARCH__)
   fill_fast_const_i(&h_fast_const_i, T);
+#if defined(ADP_CORNER_TABLE)
+  {
+    static const IntTables* built_for = nullptr;
+    static int32_t* table = nullptr;
+    if (built_for != T) {
+      if (!table) table = new int32_t[kCornerEntriesI];
+      build_corner_table_i(T, table);
+      built_for = T;
+    }
+    h_fast_const_i.corner = table;
+  }
+#endif
 #endif
 }
 
@@ -394,11 +429,19 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
               if (u1 <= u1cap && u2 <= u2cap && u1 + u2 <= room) {
                 const int k = i + 1 + u1, l = j - 1 - u2;
                 const int v = C[t4(k, l)];
+#if defined(ADP_CORNER_TABLE)
+                if (v < kInfHalf) {
+                  const int cin = (cn[l] << 4) | cp[k];
+                  p2 = ADP_FCI.corner + ((size_t)q << 16) + ((size_t)codeij << 8) + cin;
+                  a2 = v + H.RI[cin];
+                }
+#else
                 if (v < kInfHalf) {
                   int add;
                   p2 = mfe_corner_entry(H, P, q, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1], &add);
                   a2 = v + H.RI[(cn[l] << 4) | cp[k]] + add;
                 }
+#endif
               }
               const int t2 = *p2;
               other = imin(other, cadd + ctab);

@@ -95,7 +95,38 @@ struct PfHot {                        // shared memory, staged once per CTA
 struct FastConst {
   double ip[32];                      // [parity][q]: interior[s] * scale[s+2] of level s = 4 + parity + 2q (0 beyond kMaxLoop)
   double nin[32];                     // [parity][q]: ninio factor of asymmetry s - 4
+#if defined(ADP_CORNER_TABLE)
+  const double* corner;               // see build_corner_table
+#endif
 };
+
+// EXPERIMENT, off in the product build (-DADP_CORNER_TABLE; prepared without a GPU, checked in host emulation only -- first
+// thing to time in the next round).  The weight of corner candidate q = 1..8 depends on eight nucleotides
+// only, and the cell already holds them as two bytes: the closing pair's code (nucleotide + 3' neighbour of i, nucleotide +
+// 5' neighbour of j) and the inner pair's code (the same of l and k), the byte it looks RI up with.  One table of
+// 8 x 256 x 256 doubles (4 MB, L2-resident), indexed [q-1][closing code][inner code] and holding
+// scale[u1+u2+2] * interior_x(...), replaces the per-candidate type / neighbour decoding and the six-way case split of
+// corner_entry: every lane of a group runs the same short path.
+#if defined(ADP_CORNER_TABLE)
+constexpr size_t kCornerEntries = (size_t)8 << 16;
+inline void build_corner_table(const PfTables* T, double* out) {
+  for (int q = 1; q < 9; q++) {
+    const int u1 = (int)((0x322211100ull >> (4 * q)) & 15), u2 = (int)((0x232121010ull >> (4 * q)) & 15);
+    for (int co = 0; co < 256; co++) {
+      const int a = co >> 4, b = co & 15;
+      const int si = (a >> 2) + 1, si1 = (a & 3) + 1, sj = (b >> 2) + 1, sj1 = (b & 3) + 1;
+      const int type = pair_type(si, sj);
+      for (int ci = 0; ci < 256; ci++) {
+        const int a2 = ci >> 4, b2 = ci & 15;      // cn[l], cp[k]
+        const int sl = (a2 >> 2) + 1, sl1 = (a2 & 3) + 1, sk = (b2 >> 2) + 1, sk1 = (b2 & 3) + 1;
+        const int t2 = pair_type(sk, sl);
+        out[((size_t)(q - 1) << 16) | ((size_t)co << 8) | ci] =
+            (type && t2) ? T->scale[u1 + u2 + 2] * interior_x(*T, T, u1, u2, type, rtype(t2), si1, sj1, sk1, sl1) : 0.;
+      }
+    }
+  }
+}
+#endif
 
 ADP_HD void fill_fast_const(FastConst* fc, const PfTables* T) {
   for (int t = 0; t < 32; t++) {
@@ -169,6 +200,18 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
   }
 #if !defined(__CUDA_ARCH__)
   fill_fast_const(&h_fast_const, T);
+#if defined(ADP_CORNER_TABLE)
+  {
+    static const PfTables* built_for = nullptr;
+    static double* table = nullptr;
+    if (built_for != T) {
+      if (!table) table = new double[kCornerEntries];
+      build_corner_table(T, table);
+      built_for = T;
+    }
+    h_fast_const.corner = table;
+  }
+#endif
 #endif
 }
 
@@ -606,6 +649,9 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               const double v = qb[t4(i + 1, j - 1)] * H.RI[(cn[j - 1] << 4) | cp[i + 1]];
               other += v * H.cfac[0] * H.stack[type * 8 + H.tyr[codeij]];
             }
+#if defined(ADP_CORNER_TABLE)
+            const double* const ctq = ADP_FC.corner + ((size_t)codeij << 8) - ((size_t)1 << 16);
+#endif
             ADP_NOUNROLL
             for (int q = 1 + sub; q < 9; q += Gs) {
               int u1, u2;
@@ -614,12 +660,21 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               const double* p2 = zp;
               if (u1 <= u1cap && u2 <= u2cap && u1 + u2 <= room) {
                 const int k = i + 1 + u1, l = j - 1 - u2;
+#if defined(ADP_CORNER_TABLE)
+                const int cin = (cn[l] << 4) | cp[k];
+                const double v = qb[t4(k, l)] * H.RI[cin];
+                if (v != 0.) {
+                  p2 = ctq + ((size_t)q << 16) + cin;
+                  v2 = v;
+                }
+#else
                 const double v = qb[t4(k, l)] * H.RI[(cn[l] << 4) | cp[k]];
                 if (v != 0.) {
                   double fac;
                   p2 = corner_entry(H, G, q, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1], &fac);
                   v2 = v * fac;
                 }
+#endif
               }
               const double t2 = *p2;
               other += cval * ctab;
@@ -958,12 +1013,21 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
               const double* p2 = zp;
               if (u1 <= u1cap && u2 <= u2cap) {
                 const int i = k - 1 - u1, j = l + 1 + u2;
+#if defined(ADP_CORNER_TABLE)
+                const int cout = (cn[i] << 4) | cp[j];
+                const double v = qb[t4(i, j)] * H.RI[cout];
+                if (v != 0.) {
+                  p2 = ADP_FC.corner + ((size_t)(q - 1) << 16) + ((size_t)cout << 8) + codekl;
+                  v2 = v;
+                }
+#else
                 const double v = qb[t4(i, j)] * H.RI[(cn[i] << 4) | cp[j]];
                 if (v != 0.) {
                   double fac;
                   p2 = corner_entry(H, G, q, pair_type(c.S[i], c.S[j]), t2r, c.S[i + 1], c.S[j - 1], sp1, sq1, &fac);
                   v2 = v * fac;
                 }
+#endif
               }
               const double t2 = *p2;
               other += cval * ctab;

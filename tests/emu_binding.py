@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 class Emu:
     def __init__(self, par=None):
-        L = self.lib = C.CDLL(os.path.join(HERE, "emu", "libadp_emu.so"))
+        # ADP_EMU_LIB: an emulation build with experiment switches (e.g. -DADP_CORNER_TABLE), for checking them without a GPU
+        L = self.lib = C.CDLL(os.environ.get("ADP_EMU_LIB") or os.path.join(HERE, "emu", "libadp_emu.so"))
         L.emu_model_load.restype = C.c_void_p
         L.emu_model_load.argtypes = [C.c_char_p]
         L.emu_error.restype = C.c_char_p
