@@ -88,6 +88,7 @@ struct CtaExec {
     if (g > 1) { a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1); }
   }
   __device__ __forceinline__ int atomic_inc(int* ctr) const { return atomicAdd(ctr, 1); }
+  __device__ __forceinline__ double shfl_down_d(double v, int o) const { return __shfl_down_sync(0xffffffffu, v, o); }
   __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
 };
 #endif
@@ -113,6 +114,7 @@ struct SerialExec {
   void group_sum2_rt(double&, double&, int) const {}
   int group_min_rt(int v, int) const { return v; }
   int atomic_inc(int* ctr) const { return (*ctr)++; }
+  double shfl_down_d(double v, int) const { return v; }
   void warp_sync() const {}
 };
 

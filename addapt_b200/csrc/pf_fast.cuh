@@ -215,7 +215,15 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
 #endif
 }
 
+// EXPERIMENT, off in the product build (-DADP_QM_SCAN; prepared without a GPU, checked in host emulation only, DESIGN.md
+// section 7): the unpaired-prefix half of Qm(i,j), U(i) = sum_u eMLb^u Qm1(i+u,j), obeys U(i) = [i may stay unpaired] eMLb
+// (Qm1(i+1,j) + U(i+1)): one warp evaluates it for the whole column as a scan (two more vectors, by column parity), and the
+// dot products of the chunk queue keep only the other half of their terms.
+#if defined(ADP_QM_SCAN)
+constexpr int kFastVectors = 18;
+#else
 constexpr int kFastVectors = 16;
+#endif
 
 struct FastWork {
   double* qb;      // Qb, then (outside) the outside weights: trimmed triangle
@@ -568,6 +576,42 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     ADP_TICK(5)
   };
 
+#if defined(ADP_QM_SCAN)
+  // U(., jq) for the finished Qm1 column jq, by one warp: every lane folds a block of rows into an affine map, a suffix scan
+  // over the lanes composes the maps, a second pass over the block writes the values
+  auto scan_unpaired = [&](int jq) {
+    const int nrq = jq - 4;
+    if (nrq < 1) return;
+    double* Uv = w.vecp(16 + (jq & 1));
+    const double* x = w.vecp(qm1_slot(jq));
+    const int lane = ex.lane();
+    const int B = (nrq + E::kWarp - 1) / E::kWarp;
+    const int lo = lane * B + 1;
+    int hi = lo + B - 1;
+    if (hi > nrq) hi = nrq;
+    double A = 1., Cc = 0.;                       // U(lo) = A * U(hi+1) + Cc
+    ADP_NOUNROLL
+    for (int i = hi; i >= lo; i--) {
+      const double m = (i < nrq && (!kCst || can_unpair(c, i))) ? eb1 : 0.;      // U(nrq) = 0: no row below it
+      Cc = m * (Cc + x[i + 1]);
+      A = m * A;
+    }
+    ADP_NOUNROLL
+    for (int o = 1; o < E::kWarp; o <<= 1) {      // higher lanes hold the higher rows: suffix scan
+      const double A2 = ex.shfl_down_d(A, o), C2 = ex.shfl_down_d(Cc, o);
+      if (lane + o < E::kWarp) { Cc = A * C2 + Cc; A = A * A2; }
+    }
+    double un = ex.shfl_down_d(Cc, 1);            // U at the first row of the next lane's block
+    if (lane + 1 >= E::kWarp) un = 0.;
+    ADP_NOUNROLL
+    for (int i = hi; i >= lo; i--) {
+      const double m = (i < nrq && (!kCst || can_unpair(c, i))) ? eb1 : 0.;
+      un = m * (un + x[i + 1]);
+      Uv[i] = un;
+    }
+  };
+#endif
+
   // Qm(., jq) from the finished Qm1 column jq: row pairs (rows paired so that every pair sums the same number of terms), a few
   // lanes per pair, a warp-sized chunk of pairs at a time from the queue.  Qm(., jq) is first read by column jq + 5.
   auto drain_qm = [&](int jq) {
@@ -586,6 +630,18 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       const bool valid = slot < npair;
       const int iA = slot + 1, iB = nrq - slot;       // iA <= iB; equal for the middle row of an odd count
       double tA = 0., tB = 0.;
+#if defined(ADP_QM_SCAN)
+      const double* Uq = w.vecp(16 + (jq & 1));
+      if (valid) {      // run = 0: the unpaired-prefix terms come from the scan
+        tA = qm_row_terms(qm, qm1q, eMLbS, iA, nrq, 0, subC, Gc);
+        if (iB > iA) tB = qm_row_terms(qm, qm1q, eMLbS, iB, nrq, 0, subC, Gc);
+      }
+      ex.group_sum2_rt(tA, tB, Gc);
+      if (valid && subC == 0) {
+        qm[t4(iA, jq)] = tA + qm1q[iA] + Uq[iA];
+        if (iB > iA) qm[t4(iB, jq)] = tB + qm1q[iB] + Uq[iB];
+      }
+#else
       if (valid) {
         tA = qm_row_terms(qm, qm1q, eMLbS, iA, nrq, kCst ? (int)c.upr[iA] : 1000, subC, Gc);
         if (iB > iA) tB = qm_row_terms(qm, qm1q, eMLbS, iB, nrq, kCst ? (int)c.upr[iB] : 1000, subC, Gc);
@@ -595,6 +651,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         qm[t4(iA, jq)] = tA + qm1q[iA];
         if (iB > iA) qm[t4(iB, jq)] = tB + qm1q[iB];
       }
+#endif
     }
   };
 
@@ -750,6 +807,9 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     // ---- interval 2: premultiplied vectors of the new column; exterior prefix; preparation of column j+1; what is left
     //      of the deferred work
     {
+#if defined(ADP_QM_SCAN)
+      if (ex.warp() == (nt >> warp_lg) - 1) scan_unpaired(j);
+#endif
       double* x1n_wr = w.vecp(4 + (j & 1));
       const int cnj = cn[j] << 4;
       ADP_NOUNROLL
