@@ -69,7 +69,7 @@ class Problem:
 
 
 def library_path():
-    # ADDAPT_B200_LIB: an instrumented build of the same engine (tools/phase_profile.sh), for tuning runs only
+    # ADDAPT_B200_LIB: an instrumented build of the same engine (tools/variant_build.sh), for tuning runs only
     return os.environ.get("ADDAPT_B200_LIB") or os.path.join(HERE, "libaddapt_b200.so")
 
 

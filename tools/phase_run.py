@@ -1,4 +1,4 @@
-"""Per-phase clock64() timing of the fast PF kernel (see tools/phase_profile.sh): runs one small fold-eval batch on the instrumented
+"""Per-phase clock64() timing of the fast PF kernel (tools/variant_build.sh prof -DADP_PHASE_PROFILE; ADDAPT_B200_LIB=build/prof/libaddapt_b200_prof.so): runs one small fold-eval batch on the instrumented
 build; the kernel prints, for every warp of CTA 0, the cycles spent in each phase of the column loop."""
 import sys
 sys.path.insert(0, '.')
