@@ -1,15 +1,18 @@
 #!/usr/bin/env python3
-"""Static SASS size of pf_fast_kernel<256,true,false> by source region of pf_fast.cuh (the instruction caches are small --
+"""Static SASS size of pf_fast_kernel<256,true,false> (or, with --kernel=mfe, mfe_fast_kernel<256,true>) by source region of pf_fast.cuh / mfe_fast.cuh (the instruction caches are small --
 L0 ~6 KB, L1.5 32 KB per SM -- so the hot loop bodies are kept compact).   python tools/code_size.py [lib.so]"""
 import collections, os, re, subprocess, sys, tempfile
-lib = sys.argv[1] if len(sys.argv) > 1 else "addapt_b200/libaddapt_b200.so"
-src_path = "addapt_b200/csrc/pf_fast.cuh"
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+KERNEL = "mfe" if "--kernel=mfe" in sys.argv else "pf"
+lib = args[0] if args else "addapt_b200/libaddapt_b200.so"
+src_path = "addapt_b200/csrc/%s_fast.cuh" % KERNEL
+src_name = os.path.basename(src_path)
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "fold_kernels", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 sass = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
 sec = [i for i, l in enumerate(sass) if re.match(r"\s*\.section\s*\.text\.", l)]
-a = [i for i in sec if "pf_fast_kernelILi256ELb1ELb0" in sass[i]][0]
+a = [i for i in sec if ("pf_fast_kernelILi256ELb1ELb0" if KERNEL == "pf" else "mfe_fast_kernelILi256ELb1") in sass[i]][0]
 b = min(i for i in sec + [len(sass)] if i > a)
 instrs, chain, pend = [], [], []
 for ln in sass[a:b]:
@@ -27,7 +30,10 @@ def find(sub, start=0):
         if sub in src[i]:
             return i + 1
     return None
-ins_a, out_a = find("ADP_HD double fast_inside("), find("ADP_HD void fast_outside(")
+if KERNEL == "pf":
+    ins_a, out_a = find("ADP_HD double fast_inside("), find("ADP_HD void fast_outside(")
+else:
+    ins_a, out_a = find("ADP_HD int mfe_fast_fill("), len(src) + 1
 MI = [("ADP_HD double fast_inside(", "in.init"), ("auto prepare_column", "in.levels"), ("double* ext_n", "in.rows"), ("auto drain_qm", "in.qm"),
       ("// j = 4 is a warm-up", "in.colhead"), ("// ---- interval 1: Qb(i,j)", "in.cells.head"), ("// corner candidates through", "in.cells.corners"),
       ("// bulges with the unpaired run on the 3' side", "in.cells.axis"), ("// multiloop closed by (i,j)", "in.cells.ml"), ("// ---- cell total", "in.cells.fin"),
@@ -36,7 +42,14 @@ MO = [("ADP_HD void fast_outside(", "out.init"), ("auto prepare_column", "out.ca
       ("// l = n+1 is a warm-up", "out.colhead"), ("// ---- interval 1: outside weight", "out.cells.head"), ("const int t2r = rtype(type);", "out.cells.corners"),
       ("// enclosing bulges with the run on the 3' side", "out.cells.axis"), ("// (k,l) is a stem of a multiloop", "out.cells.ml"), ("// ---- cell total", "out.cells.fin"),
       ("// ---- interval 2: premultiplied", "out.int2"), ("// the motif's inner pairs", "out.motif")]
-marks = sorted([(find(s, ins_a), n) for s, n in MI if find(s, ins_a)] + [(find(s, out_a), n) for s, n in MO if find(s, out_a)])
+MM = [("ADP_HD int mfe_fast_fill(", "fill.init"), ("auto prepare_column", "fill.levels"), ("      const int prev = fm1_prev[r + 1];", "fill.rows"),
+      ("// j = 4 is a warm-up", "fill.colhead"), ("// ---- interval 1: C(i,j)", "fill.cells.head"), ("// corner candidates, software-pipelined", "fill.cells.corners"),
+      ("// the four 1-D filters along", "fill.cells.axis"), ("int k = i + 6 + sub;", "fill.cells.ml"), ("other = imin(other, cadd + ctab);", "fill.cells.fin"),
+      ("// ---- interval 2: shifted copies", "fill.int2")]
+if KERNEL == "pf":
+    marks = sorted([(find(s, ins_a), n) for s, n in MI if find(s, ins_a)] + [(find(s, out_a), n) for s, n in MO if find(s, out_a)])
+else:
+    marks = sorted([(find(s, ins_a), n) for s, n in MM if find(s, ins_a)])
 def rname(l):
     nm = "other"
     for a_, n in marks:
@@ -45,7 +58,7 @@ def rname(l):
     return nm
 agg = collections.Counter()
 for c in instrs:
-    best = next((l for f, l in c if f == "pf_fast.cuh" and l >= ins_a), None)
+    best = next((l for f, l in c if f == src_name and l >= ins_a), None)
     agg[rname(best) if best else "other"] += 1
 for k, v in agg.most_common():
     print("%-20s %5d instr %6.1f KB" % (k, v, v * 16 / 1024))
