@@ -393,7 +393,7 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
         const int l = j + 2 - S;
         w.lvoff[t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(int32_t);
       }
-      const int lg = group_lg(m, nt_lg, warp_lg);
+      const int lg = group_lg(m, nt_lg, ADP_CELL_GROUP_CAP_LG);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const int32_t* x1n_rd = w.vecp(4 + (j & 1));     // column j-2
       const int upl_j1 = kCst ? (int)c.upl[j - 1] : 1000;

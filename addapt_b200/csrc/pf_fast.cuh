@@ -270,6 +270,12 @@ ADP_HD int ilog2_floor(unsigned v) {
 #endif
 }
 
+// Largest lane group of the per-cell phase (log2).  The product build uses up to a warp; -DADP_CELL_GROUP_CAP_LG=3 (or 4) is an
+// untimed experiment: columns with few cells would trade the last shuffle rounds of the reduction for one more loop iteration.
+#if !defined(ADP_CELL_GROUP_CAP_LG)
+#define ADP_CELL_GROUP_CAP_LG warp_lg
+#endif
+
 // log2 of the lanes per cell such that m cells fill (at most) a CTA of 2^nt_lg threads; at most a warp per cell
 ADP_HD int group_lg(int m, int nt_lg, int cap_lg) {
   int lg = nt_lg;
@@ -675,7 +681,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         const int l = j + 2 - S;
         w.lvoff[t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(double);
       }
-      const int lg = group_lg(m, nt_lg, warp_lg);
+      const int lg = group_lg(m, nt_lg, ADP_CELL_GROUP_CAP_LG);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const double* x1n_rd = w.vecp(4 + (j & 1));     // column j-2
       const int upl_j1 = kCst ? (int)c.upl[j - 1] : 1000;
@@ -1030,7 +1036,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         const int j = l + S - 2;
         w.lvoff[t] = (((j - 4) * (j - 5)) >> 1) * (int)sizeof(double);
       }
-      const int lg = group_lg(m, nt_lg, warp_lg);
+      const int lg = group_lg(m, nt_lg, ADP_CELL_GROUP_CAP_LG);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const double* x1n_rd = w.vecp(4 + (l & 1));        // column l+2
       const int upr_l1 = kCst ? (int)c.upr[l + 1] : n - l;
