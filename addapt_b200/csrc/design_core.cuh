@@ -139,11 +139,7 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
       job.n_query = 0;
       job.qi = nullptr; job.qj = nullptr; job.qprobs = nullptr;
       if constexpr (kFast) {
-#if defined(ADP_DESIGN_ONE_CST)
-        if (!run_pf_job_fast<E, true>(ex, job, fold_small, mats, dstate)) {
-#else
         if (!run_pf_job_fast(ex, job, fold_small, mats, dstate)) {
-#endif
           if (declined) *declined = true;
           return 0.;
         }

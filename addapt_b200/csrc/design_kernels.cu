@@ -127,10 +127,8 @@ LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs, bool fast) {
 static cudaError_t upload_fast_const(const PfTables* host_tables, cudaStream_t stream) {
   FastConst fc;
   fill_fast_const(&fc, host_tables);
-#if defined(ADP_CORNER_TABLE)
   fc.corner = device_corner_table(host_tables);
   if (!fc.corner) return cudaErrorMemoryAllocation;
-#endif
   return cudaMemcpyToSymbolAsync(c_fast_const, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
 }
 

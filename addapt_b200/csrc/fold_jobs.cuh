@@ -87,11 +87,7 @@ ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats)
 // fast_matrix_doubles(n) doubles (shared or global); `dstate`: host emulation only.  Returns false (on every
 // thread, nothing written) when the sequence holds a letter outside ACGU/T -- the caller then uses run_pf_job.
 // `qm_ext` (optional): put Qm there (global scratch, t4_count(n)+2 doubles) instead of behind Qb in `mats`.
-// kOneCstPath (EXPERIMENT for the score / Monte-Carlo kernels, -DADP_DESIGN_ONE_CST, off in the product build, prepared without a
-// GPU): fold unconstrained jobs through the constrained instantiation too (it is valid for them: the run lengths then span the
-// sequence and every pair is allowed), so that a kernel that alternates constrained and unconstrained fills keeps ONE copy of the
-// sweep hot in the 32 KB instruction cache instead of two.
-template <class E, bool kOneCstPath = false>
+template <class E>
 ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* mats, double* dstate = nullptr, double* qm_ext = nullptr) {
   const int n = job.n;
 #if defined(ADP_PHASE_PROFILE) && defined(__CUDA_ARCH__)
@@ -132,7 +128,7 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   if (blockIdx.x == 0 && threadIdx.x == 0) printf("prologue %lld cycles\n", clock64() - tp0_);
 #endif
 
-  const double Z = (kOneCstPath || c.has_cst) ? fast_inside<true>(ex, c, *H, job.T, mboltz, w) : fast_inside<false>(ex, c, *H, job.T, mboltz, w);
+  const double Z = c.has_cst ? fast_inside<true>(ex, c, *H, job.T, mboltz, w) : fast_inside<false>(ex, c, *H, job.T, mboltz, w);
   if (ex.tid() == 0)
     *job.dG = Z > 0. ? (-log(Z) - n * log(job.T->pf_scale)) * job.T->kT / 1000. : (double)INFINITY;
   if (!job.outside) return true;
@@ -143,7 +139,7 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   out.qj = job.qj;
   out.qprobs = job.qprobs;
   if (Z > 0.) {
-    if (kOneCstPath || c.has_cst) fast_outside<true>(ex, c, *H, job.T, job.motif, mboltz, w, out);
+    if (c.has_cst) fast_outside<true>(ex, c, *H, job.T, job.motif, mboltz, w, out);
     else fast_outside<false>(ex, c, *H, job.T, job.motif, mboltz, w, out);
   } else {
     if (job.bppm)

@@ -283,8 +283,7 @@ LaunchPlan plan_pf_fast(const DeviceInfo& d, int n, int jobs) {
   return p;
 }
 
-#if defined(ADP_CORNER_TABLE)
-// experiment (pf_fast.cuh, build_corner_table): the table of the current device, built and uploaded on first use
+// code-indexed corner table (pf_fast.cuh, build_corner_table): the table of the current device, built and uploaded on first use
 const double* device_corner_table(const PfTables* host_tables) {
   static double* tables[64] = {nullptr};
   int dev = 0;
@@ -299,15 +298,12 @@ const double* device_corner_table(const PfTables* host_tables) {
   }
   return tables[dev];
 }
-#endif
 
 cudaError_t launch_pf_fast(const PfBatchArgs& a, const LaunchPlan& p, const PfTables* host_tables, cudaStream_t stream) {
   FastConst fc;
   fill_fast_const(&fc, host_tables);
-#if defined(ADP_CORNER_TABLE)
   fc.corner = device_corner_table(host_tables);
   if (!fc.corner) return cudaErrorMemoryAllocation;
-#endif
   cudaError_t ce = cudaMemcpyToSymbolAsync(c_fast_const, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
   if (ce != cudaSuccess) return ce;
   if (p.threads == 256) {
@@ -340,7 +336,6 @@ LaunchPlan plan_mfe_fast(const DeviceInfo& d, int n, int jobs) {
   return p;
 }
 
-#if defined(ADP_CORNER_TABLE)
 static const int32_t* device_corner_table_i(const IntTables* host_tables) {
   static int32_t* tables[64] = {nullptr};
   int dev = 0;
@@ -355,15 +350,12 @@ static const int32_t* device_corner_table_i(const IntTables* host_tables) {
   }
   return tables[dev];
 }
-#endif
 
 cudaError_t launch_mfe_fast(const MfeBatchArgs& a, const LaunchPlan& p, const IntTables* host_tables, cudaStream_t stream) {
   FastConstI fc;
   fill_fast_const_i(&fc, host_tables);
-#if defined(ADP_CORNER_TABLE)
   fc.corner = device_corner_table_i(host_tables);
   if (!fc.corner) return cudaErrorMemoryAllocation;
-#endif
   cudaError_t ce = cudaMemcpyToSymbolAsync(c_fast_const_i, &fc, sizeof fc, 0, cudaMemcpyHostToDevice, stream);
   if (ce != cudaSuccess) return ce;
   if (p.threads == 256) {

@@ -67,8 +67,6 @@ LaunchPlan plan_mfe(const DeviceInfo&, int n, int jobs);
 cudaError_t launch_pf(const PfBatchArgs&, const LaunchPlan&, cudaStream_t);
 cudaError_t launch_mfe(const MfeBatchArgs&, const LaunchPlan&, cudaStream_t);
 cudaError_t launch_dfma_probe(double* out, int iters, int grid, int threads, cudaStream_t);
-#if defined(ADP_CORNER_TABLE)
-const double* device_corner_table(const PfTables* host_tables);     // experiment, see pf_fast.cuh build_corner_table
-#endif
+const double* device_corner_table(const PfTables* host_tables);     // see pf_fast.cuh build_corner_table
 
 }  // namespace adp

@@ -35,12 +35,9 @@ struct MfeHot {                       // shared memory, staged once per job
 struct FastConstI {
   int32_t ip[32];                     // [parity][q]: interior[s] of level s = 4 + parity + 2q (kInf beyond kMaxLoop)
   int32_t nin[32];                    // [parity][q]: ninio(s - 4)
-#if defined(ADP_CORNER_TABLE)
-  const int32_t* corner;              // experiment, see build_corner_table in pf_fast.cuh: [q-1][closing code][inner code] energies
-#endif
+  const int32_t* corner;              // code-indexed corner table (build_corner_table_i): [q-1][closing code][inner code] energies
 };
 
-#if defined(ADP_CORNER_TABLE)
 constexpr size_t kCornerEntriesI = (size_t)9 << 16;      // all nine candidates (the MFE loop keeps the stack in the loop)
 inline void build_corner_table_i(const IntTables* T, int32_t* out) {
   for (int q = 0; q < 9; q++) {
@@ -58,7 +55,6 @@ inline void build_corner_table_i(const IntTables* T, int32_t* out) {
     }
   }
 }
-#endif
 
 ADP_HD void fill_fast_const_i(FastConstI* fc, const IntTables* T) {
   for (int t = 0; t < 32; t++) {
@@ -111,7 +107,6 @@ ADP_HD void stage_mfe_hot(const E& ex, MfeHot* H, const IntTables* T) {
   }
 #if !defined(__CUDA_ARCH__)
   fill_fast_const_i(&h_fast_const_i, T);
-#if defined(ADP_CORNER_TABLE)
   {
     static const IntTables* built_for = nullptr;
     static int32_t* table = nullptr;
@@ -122,7 +117,6 @@ ADP_HD void stage_mfe_hot(const E& ex, MfeHot* H, const IntTables* T) {
     }
     h_fast_const_i.corner = table;
   }
-#endif
 #endif
 }
 
@@ -393,7 +387,7 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
         const int l = j + 2 - S;
         w.lvoff[t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(int32_t);
       }
-      const int lg = group_lg(m, nt_lg, ADP_CELL_GROUP_CAP_LG);
+      const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const int32_t* x1n_rd = w.vecp(4 + (j & 1));     // column j-2
       const int upl_j1 = kCst ? (int)c.upl[j - 1] : 1000;
@@ -429,19 +423,11 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
               if (u1 <= u1cap && u2 <= u2cap && u1 + u2 <= room) {
                 const int k = i + 1 + u1, l = j - 1 - u2;
                 const int v = C[t4(k, l)];
-#if defined(ADP_CORNER_TABLE)
                 if (v < kInfHalf) {
                   const int cin = (cn[l] << 4) | cp[k];
                   p2 = ADP_FCI.corner + ((size_t)q << 16) + ((size_t)codeij << 8) + cin;
                   a2 = v + H.RI[cin];
                 }
-#else
-                if (v < kInfHalf) {
-                  int add;
-                  p2 = mfe_corner_entry(H, P, q, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1], &add);
-                  a2 = v + H.RI[(cn[l] << 4) | cp[k]] + add;
-                }
-#endif
               }
               const int t2 = *p2;
               other = imin(other, cadd + ctab);

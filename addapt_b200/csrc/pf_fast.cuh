@@ -95,19 +95,15 @@ struct PfHot {                        // shared memory, staged once per CTA
 struct FastConst {
   double ip[32];                      // [parity][q]: interior[s] * scale[s+2] of level s = 4 + parity + 2q (0 beyond kMaxLoop)
   double nin[32];                     // [parity][q]: ninio factor of asymmetry s - 4
-#if defined(ADP_CORNER_TABLE)
   const double* corner;               // see build_corner_table
-#endif
 };
 
-// EXPERIMENT, off in the product build (-DADP_CORNER_TABLE; prepared without a GPU, checked in host emulation only -- first
-// thing to time in the next round).  The weight of corner candidate q = 1..8 depends on eight nucleotides
-// only, and the cell already holds them as two bytes: the closing pair's code (nucleotide + 3' neighbour of i, nucleotide +
+// Code-indexed corner table (round 2: +11 % fold-evals/s, +10 % MFE folds/s over per-candidate decoding, profiles/r2_experiments.md).
+// The weight of corner candidate q = 1..8 depends on eight nucleotides only, and the cell already holds them as two bytes: the closing pair's code (nucleotide + 3' neighbour of i, nucleotide +
 // 5' neighbour of j) and the inner pair's code (the same of l and k), the byte it looks RI up with.  One table of
 // 8 x 256 x 256 doubles (4 MB, L2-resident), indexed [q-1][closing code][inner code] and holding
 // scale[u1+u2+2] * interior_x(...), replaces the per-candidate type / neighbour decoding and the six-way case split of
 // corner_entry: every lane of a group runs the same short path.
-#if defined(ADP_CORNER_TABLE)
 constexpr size_t kCornerEntries = (size_t)8 << 16;
 inline void build_corner_table(const PfTables* T, double* out) {
   for (int q = 1; q < 9; q++) {
@@ -126,7 +122,6 @@ inline void build_corner_table(const PfTables* T, double* out) {
     }
   }
 }
-#endif
 
 ADP_HD void fill_fast_const(FastConst* fc, const PfTables* T) {
   for (int t = 0; t < 32; t++) {
@@ -200,7 +195,6 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
   }
 #if !defined(__CUDA_ARCH__)
   fill_fast_const(&h_fast_const, T);
-#if defined(ADP_CORNER_TABLE)
   {
     static const PfTables* built_for = nullptr;
     static double* table = nullptr;
@@ -212,18 +206,12 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
     h_fast_const.corner = table;
   }
 #endif
-#endif
 }
 
-// EXPERIMENT, off in the product build (-DADP_QM_SCAN; prepared without a GPU, checked in host emulation only, DESIGN.md
-// section 7): the unpaired-prefix half of Qm(i,j), U(i) = sum_u eMLb^u Qm1(i+u,j), obeys U(i) = [i may stay unpaired] eMLb
+// The unpaired-prefix half of Qm(i,j), U(i) = sum_u eMLb^u Qm1(i+u,j), obeys U(i) = [i may stay unpaired] eMLb
 // (Qm1(i+1,j) + U(i+1)): one warp evaluates it for the whole column as a scan (two more vectors, by column parity), and the
 // dot products of the chunk queue keep only the other half of their terms.
-#if defined(ADP_QM_SCAN)
 constexpr int kFastVectors = 18;
-#else
-constexpr int kFastVectors = 16;
-#endif
 
 struct FastWork {
   double* qb;      // Qb, then (outside) the outside weights: trimmed triangle
@@ -269,12 +257,6 @@ ADP_HD int ilog2_floor(unsigned v) {
   return 31 - __builtin_clz(v);
 #endif
 }
-
-// Largest lane group of the per-cell phase (log2).  The product build uses up to a warp; -DADP_CELL_GROUP_CAP_LG=3 (or 4) is an
-// untimed experiment: columns with few cells would trade the last shuffle rounds of the reduction for one more loop iteration.
-#if !defined(ADP_CELL_GROUP_CAP_LG)
-#define ADP_CELL_GROUP_CAP_LG warp_lg
-#endif
 
 // log2 of the lanes per cell such that m cells fill (at most) a CTA of 2^nt_lg threads; at most a warp per cell
 ADP_HD int group_lg(int m, int nt_lg, int cap_lg) {
@@ -582,7 +564,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     ADP_TICK(5)
   };
 
-#if defined(ADP_QM_SCAN)
   // U(., jq) for the finished Qm1 column jq, by one warp: every lane folds a block of rows into an affine map, a suffix scan
   // over the lanes composes the maps, a second pass over the block writes the values
   auto scan_unpaired = [&](int jq) {
@@ -616,7 +597,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       Uv[i] = un;
     }
   };
-#endif
 
   // Qm(., jq) from the finished Qm1 column jq: row pairs (rows paired so that every pair sums the same number of terms), a few
   // lanes per pair, a warp-sized chunk of pairs at a time from the queue.  Qm(., jq) is first read by column jq + 5.
@@ -636,7 +616,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       const bool valid = slot < npair;
       const int iA = slot + 1, iB = nrq - slot;       // iA <= iB; equal for the middle row of an odd count
       double tA = 0., tB = 0.;
-#if defined(ADP_QM_SCAN)
       const double* Uq = w.vecp(16 + (jq & 1));
       if (valid) {      // run = 0: the unpaired-prefix terms come from the scan
         tA = qm_row_terms(qm, qm1q, eMLbS, iA, nrq, 0, subC, Gc);
@@ -647,17 +626,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         qm[t4(iA, jq)] = tA + qm1q[iA] + Uq[iA];
         if (iB > iA) qm[t4(iB, jq)] = tB + qm1q[iB] + Uq[iB];
       }
-#else
-      if (valid) {
-        tA = qm_row_terms(qm, qm1q, eMLbS, iA, nrq, kCst ? (int)c.upr[iA] : 1000, subC, Gc);
-        if (iB > iA) tB = qm_row_terms(qm, qm1q, eMLbS, iB, nrq, kCst ? (int)c.upr[iB] : 1000, subC, Gc);
-      }
-      ex.group_sum2_rt(tA, tB, Gc);
-      if (valid && subC == 0) {
-        qm[t4(iA, jq)] = tA + qm1q[iA];
-        if (iB > iA) qm[t4(iB, jq)] = tB + qm1q[iB];
-      }
-#endif
     }
   };
 
@@ -681,7 +649,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         const int l = j + 2 - S;
         w.lvoff[t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(double);
       }
-      const int lg = group_lg(m, nt_lg, ADP_CELL_GROUP_CAP_LG);
+      const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const double* x1n_rd = w.vecp(4 + (j & 1));     // column j-2
       const int upl_j1 = kCst ? (int)c.upl[j - 1] : 1000;
@@ -712,9 +680,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               const double v = qb[t4(i + 1, j - 1)] * H.RI[(cn[j - 1] << 4) | cp[i + 1]];
               other += v * H.cfac[0] * H.stack[type * 8 + H.tyr[codeij]];
             }
-#if defined(ADP_CORNER_TABLE)
             const double* const ctq = ADP_FC.corner + ((size_t)codeij << 8) - ((size_t)1 << 16);
-#endif
             ADP_NOUNROLL
             for (int q = 1 + sub; q < 9; q += Gs) {
               int u1, u2;
@@ -723,21 +689,12 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               const double* p2 = zp;
               if (u1 <= u1cap && u2 <= u2cap && u1 + u2 <= room) {
                 const int k = i + 1 + u1, l = j - 1 - u2;
-#if defined(ADP_CORNER_TABLE)
                 const int cin = (cn[l] << 4) | cp[k];
                 const double v = qb[t4(k, l)] * H.RI[cin];
                 if (v != 0.) {
                   p2 = ctq + ((size_t)q << 16) + cin;
                   v2 = v;
                 }
-#else
-                const double v = qb[t4(k, l)] * H.RI[(cn[l] << 4) | cp[k]];
-                if (v != 0.) {
-                  double fac;
-                  p2 = corner_entry(H, G, q, type, rtype(pair_type(c.S[k], c.S[l])), si1, sj1, c.S[k - 1], c.S[l + 1], &fac);
-                  v2 = v * fac;
-                }
-#endif
               }
               const double t2 = *p2;
               other += cval * ctab;
@@ -813,9 +770,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     // ---- interval 2: premultiplied vectors of the new column; exterior prefix; preparation of column j+1; what is left
     //      of the deferred work
     {
-#if defined(ADP_QM_SCAN)
       if (ex.warp() == (nt >> warp_lg) - 1) scan_unpaired(j);
-#endif
       double* x1n_wr = w.vecp(4 + (j & 1));
       const int cnj = cn[j] << 4;
       ADP_NOUNROLL
@@ -1036,7 +991,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         const int j = l + S - 2;
         w.lvoff[t] = (((j - 4) * (j - 5)) >> 1) * (int)sizeof(double);
       }
-      const int lg = group_lg(m, nt_lg, ADP_CELL_GROUP_CAP_LG);
+      const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const double* x1n_rd = w.vecp(4 + (l & 1));        // column l+2
       const int upr_l1 = kCst ? (int)c.upr[l + 1] : n - l;
@@ -1079,21 +1034,12 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
               const double* p2 = zp;
               if (u1 <= u1cap && u2 <= u2cap) {
                 const int i = k - 1 - u1, j = l + 1 + u2;
-#if defined(ADP_CORNER_TABLE)
                 const int cout = (cn[i] << 4) | cp[j];
                 const double v = qb[t4(i, j)] * H.RI[cout];
                 if (v != 0.) {
                   p2 = ADP_FC.corner + ((size_t)(q - 1) << 16) + ((size_t)cout << 8) + codekl;
                   v2 = v;
                 }
-#else
-                const double v = qb[t4(i, j)] * H.RI[(cn[i] << 4) | cp[j]];
-                if (v != 0.) {
-                  double fac;
-                  p2 = corner_entry(H, G, q, pair_type(c.S[i], c.S[j]), t2r, c.S[i + 1], c.S[j - 1], sp1, sq1, &fac);
-                  v2 = v * fac;
-                }
-#endif
               }
               const double t2 = *p2;
               other += cval * ctab;
