@@ -97,6 +97,10 @@ def load_library():
     L.adp_engine_set_general_only.argtypes = [vp, ci]
     L.adp_kT_kcal.argtypes = [vp]
     L.adp_kT_kcal.restype = cd
+    L.adp_param_provenance.argtypes = [vp]
+    L.adp_param_provenance.restype = cs
+    L.adp_param_file.argtypes = [vp]
+    L.adp_param_file.restype = cs
     L.adp_device_count.restype = ci
     L.adp_launch_count.argtypes = [vp]
     L.adp_launch_count.restype = C.c_uint64
@@ -147,11 +151,16 @@ class Engine:
     def __init__(self, device=0, par_file=None):
         self.lib = load_library()
         h = C.c_void_p()
-        rc = self.lib.adp_engine_create(device, _b(par_file or DEFAULT_PAR), C.byref(h))
+        # explicit argument > $ADDAPT_B200_PAR > the reconstructed file shipped in params/ (the engine warns on stderr about the
+        # latter and reports it through param_provenance: its int11 / int21 / int22 tables are rule-generated)
+        par_file = par_file or os.environ.get("ADDAPT_B200_PAR") or DEFAULT_PAR
+        rc = self.lib.adp_engine_create(device, _b(par_file), C.byref(h))
         if rc != 0:
             raise EngineError("adp_engine_create failed (%d): %s" % (rc, (self.lib.adp_last_error(None) or b"").decode()))
         self.h = h
         self.kT = self.lib.adp_kT_kcal(self.h)
+        self.param_provenance = (self.lib.adp_param_provenance(self.h) or b"").decode()
+        self.param_file = (self.lib.adp_param_file(self.h) or b"").decode()
 
     def close(self):
         if getattr(self, "h", None):

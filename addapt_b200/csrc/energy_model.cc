@@ -175,6 +175,14 @@ int EnergyModel::pair_type(int a, int b) {
 
 void EnergyModel::load(const std::string& path) {
   auto secs = read_sections(path);
+  path_ = path;
+  provenance_ = "file";
+  {
+    std::ifstream head(path);
+    std::string line;
+    for (int k = 0; k < 12 && std::getline(head, line); k++)
+      if (line.find("RECONSTRUCTION") != std::string::npos) provenance_ = "reconstructed";
+  }
   IntTables& R = raw_;
   std::memset(&R, 0, sizeof R);
 

@@ -21,6 +21,10 @@ class EnergyModel {
   const IntTables& mfe() const { return mfe_; }   // dangles / multi / exterior mismatches clamped <= 0
   const PfTables& pf() const { return pf_; }
   double kT_kcal() const { return pf_.kT / 1000.; }
+  // Where the numbers came from: "file" for a parameter file as given, "reconstructed" when the file declares itself a
+  // reconstruction (the one shipped in params/: int11 / int21 / int22 are rule-generated, not the measured Turner-2004 tables).
+  const std::string& provenance() const { return provenance_; }
+  const std::string& path() const { return path_; }
 
   // Free energy (dcal/mol) of a dot-bracket structure under the dangles=2 model (≙ vrna_eval_structure).
   int eval_structure(const std::string& seq, const std::string& db) const;
@@ -35,6 +39,7 @@ class EnergyModel {
   int loop_energy(const int* S, const int* pt, int n, int i, int j) const;
   IntTables raw_{}, mfe_{};
   PfTables pf_{};
+  std::string provenance_ = "file", path_;
 };
 
 }  // namespace adp

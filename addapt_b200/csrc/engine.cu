@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -75,6 +76,7 @@ namespace {
     cudaError_t ce_ = (call);                                                                     \
     if (ce_ != cudaSuccess) {                                                                     \
       (e)->err = std::string(#call) + ": " + cudaGetErrorString(ce_);                             \
+      (e)->pending.clear(); /* queued D2H copies of a failed call must never run in a later one */ \
       return ADP_ERR_CUDA;                                                                        \
     }                                                                                             \
   } while (0)
@@ -119,6 +121,7 @@ int fail_arg(adp_engine* e, const std::string& msg) {
 
 int check_batch(adp_engine* e, int B, int n, const void* seqs) {
   if (!e) return ADP_ERR_ARG;
+  e->pending.clear();      // every batched entry point starts here: nothing queued by an earlier (failed) call survives
   if (B < 0 || !seqs) return fail_arg(e, "null or negative batch");
   if (n < 1 || n > ADP_MAX_LEN) return fail_arg(e, "sequence length must be 1.." + std::to_string(ADP_MAX_LEN));
   return ADP_OK;
@@ -191,6 +194,18 @@ int adp_engine_create(int device, const char* par_file, adp_engine** out) {
     delete e;
     return ADP_ERR_PARAM;
   }
+  if (e->model.provenance() == "reconstructed" && !std::getenv("ADDAPT_B200_QUIET")) {
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      std::fprintf(stderr,
+                   "addapt_b200: WARNING: energy parameters come from a RECONSTRUCTED Turner-2004 file (%s):\n"
+                   "addapt_b200: WARNING: int11 / int21 / int22 are rule-generated, so energies, probabilities and scores differ from\n"
+                   "addapt_b200: WARNING: ViennaRNA's (rhf(6) apo ensemble: -29.75 vs -29.58 kcal/mol).  Pass a genuine rna_turner2004.par as\n"
+                   "addapt_b200: WARNING: par_file or in $ADDAPT_B200_PAR for reference-exact numbers (adp_param_provenance() reports which).\n",
+                   e->model.path().c_str());
+    }
+  }
   auto bail = [&](const char* what, cudaError_t ce) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(ce) + " (this engine has no CPU fallback)";
     delete e;
@@ -250,6 +265,8 @@ int adp_engine_sync(adp_engine* e) {
   return ADP_OK;
 }
 double adp_kT_kcal(const adp_engine* e) { return e ? e->model.kT_kcal() : 0.; }
+const char* adp_param_provenance(const adp_engine* e) { return e ? e->model.provenance().c_str() : ""; }
+const char* adp_param_file(const adp_engine* e) { return e ? e->model.path().c_str() : ""; }
 uint64_t adp_launch_count(const adp_engine* e) { return e ? e->launches : 0; }
 
 int adp_eval_structure(adp_engine* e, const char* seq, const char* structure, int32_t* e_dcal) {

@@ -210,11 +210,12 @@ def main():
     from addapt_b200.capi import Problem
 
     torch.cuda.set_device(local)
-    # stdout carries ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/WARN/INFO, so logging is off
-    # unless asked for explicitly, and then it goes to stderr
-    os.environ.pop("NCCL_DEBUG", None)
-    if os.environ.get("ADDAPT_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = os.environ["ADDAPT_NCCL_DEBUG"]
+    # stdout carries ONE JSON line, so NCCL's log goes to stderr -- it is NOT switched off: the communicator lines
+    # ("... rank R nranks N ...") are the record that N ranks really formed one communicator.  A caller's NCCL_DEBUG /
+    # NCCL_DEBUG_FILE are respected; the default is INFO restricted to the INIT subsystem.
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

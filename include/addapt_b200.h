@@ -51,6 +51,11 @@ int adp_engine_sync(adp_engine *);
  * ACGU-only kernels; results agree to rounding.  For parity tests of the general path. */
 int adp_engine_set_general_only(adp_engine *, int on);
 double adp_kT_kcal(const adp_engine *);                  /* fc->exp_params->kT/1000, reference scoring.cc:69,93 */
+/* Provenance of the energy tables: "file" (a parameter file used as given) or "reconstructed" (the file declares itself a
+ * reconstruction, like the one shipped in params/: int11 / int21 / int22 rule-generated -- results then differ from
+ * ViennaRNA's; adp_engine_create prints a warning on stderr unless $ADDAPT_B200_QUIET is set).  adp_param_file: its path. */
+const char *adp_param_provenance(const adp_engine *);
+const char *adp_param_file(const adp_engine *);
 int adp_device_count(void);
 uint64_t adp_launch_count(const adp_engine *);           /* kernels launched by this engine so far */
 

@@ -62,7 +62,10 @@ class Oracle:
         L.orc_pf_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(_Motif), C.c_void_p, C.c_void_p, C.c_int]
         L.orc_mfe_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(_Motif), C.c_void_p, C.c_void_p, C.c_int]
         L.orc_score_batch.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-        self.par_path = par_path or DEFAULT_PAR
+        # same precedence as the engine: explicit argument > $ADDAPT_B200_PAR > the reconstructed file in params/
+        self.par_path = par_path or os.environ.get("ADDAPT_B200_PAR") or DEFAULT_PAR
+        with open(self.par_path) as f:
+            self.param_provenance = "reconstructed" if "RECONSTRUCTION" in "".join(f.readlines()[:12]) else "file"
         self.model = L.orc_model_load(_b(self.par_path))
         if not self.model:
             raise RuntimeError("oracle: " + L.orc_error().decode())

@@ -55,3 +55,28 @@ def random_constraint(oracle, seq, rng, p_keep=0.3, p_x=0.1):
         if c[i] == "." and rng.random() < p_x:
             c[i] = "x"
     return "".join(c)
+
+
+def rnafold_symbols(bppm_tri, n):
+    """The per-position pairing string RNAfold -p prints (ViennaRNA bppm_symbol), derived from an upper-triangle bppm in the
+    layout base_pair_prob reads (reference src/scoring.cc:49-50; tri(i,j) = i*n - i*(i-1)/2 + (j-i), 0-based)."""
+    P = np.zeros((n, n))
+    iu = np.triu_indices(n)
+    P[iu] = np.asarray(bppm_tri)
+    P[np.diag_indices(n)] = 0.0
+    out = []
+    for k in range(n):
+        x1, x2 = P[k, k + 1:].sum(), P[:k, k].sum()
+        x0 = 1.0 - x1 - x2
+        if x0 > 0.667:
+            c = "."
+        elif x1 > 0.667:
+            c = "("
+        elif x2 > 0.667:
+            c = ")"
+        elif x1 + x2 > x0:
+            c = "{" if x1 / (x1 + x2) > 0.667 else "}" if x2 / (x1 + x2) > 0.667 else "|"
+        else:
+            c = "," if x0 > x1 + x2 else ":"
+        out.append(c)
+    return "".join(out)

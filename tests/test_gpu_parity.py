@@ -287,8 +287,41 @@ def test_full_size_fold_eval_properties(oracle, engine):
     e = engine.mfe(seqs, structures=False)
     assert (dg[:, 0] <= e / 100.0 + 1e-9).all()
     rng = np.random.Generator(np.random.PCG64(3))
-    idx = rng.choice(B, 256, replace=False)
-    d0 = oracle.pf_batch([seqs[i] for i in idx])
-    d1 = oracle.pf_batch([seqs[i] for i in idx], motif=cases.THEO)
+    idx = rng.choice(B, 1024, replace=False)
+    sub = [seqs[i] for i in idx]
+    d0, b0 = oracle.pf_batch(sub, bppm=True)
+    d1, b1 = oracle.pf_batch(sub, motif=cases.THEO, bppm=True)
     np.testing.assert_allclose(dg[idx, 0], d0, rtol=DG_RTOL)
     np.testing.assert_allclose(dg[idx, 1], d1, rtol=DG_RTOL)
+    # full bppm of the 1,024 sampled designs (2 x 5,050 probabilities each) against the oracle, and the queried probabilities of
+    # the full-size run against the same designs folded in a different batch (bitwise: they must not depend on the batch)
+    dg_s, pr_s, full_s = engine.fold_eval(sub, cases.THEO, queries=pairs, full=True)
+    assert np.array_equal(dg_s, dg[idx]) and np.array_equal(pr_s, pr[idx])
+    np.testing.assert_allclose(full_s[:, 0], b0, rtol=BP_RTOL, atol=BP_ATOL)
+    np.testing.assert_allclose(full_s[:, 1], b1, rtol=BP_RTOL, atol=BP_ATOL)
+    from addapt_b200.capi import tri_index
+    for k, (i, j) in enumerate(pairs):
+        np.testing.assert_allclose(pr_s[:, 0, k], b0[:, tri_index(n, i, j)], rtol=BP_RTOL, atol=BP_ATOL)
+        np.testing.assert_allclose(pr_s[:, 1, k], b1[:, tri_index(n, i, j)], rtol=BP_RTOL, atol=BP_ATOL)
+
+
+def test_reference_pairing_strings_through_the_engine(oracle, engine):
+    """reference tests/test_scoring.cc:52-55: the RNAfold -p strings of rhf(6), derived from the ENGINE's bppm.  Holo must equal
+    the reference's string; apo equals it only with a genuine parameter file (tests/test_oracle.py states the residual of the
+    reconstructed one) -- with either file the engine's string must equal the oracle's."""
+    g = json.load(open(os.path.join(GOLD, "reference_pairing_strings.json")))
+    s, n = g["seq"], len(g["seq"])
+    assert engine.param_provenance == oracle.param_provenance
+    dg, _, full = engine.fold_eval([s], cases.THEO, full=True)
+    sym = [cases.rnafold_symbols(full[0, c], n) for c in (0, 1)]
+    _, b_apo = oracle.pf(s, bppm=True)
+    _, b_holo = oracle.pf(s, motif=cases.THEO, bppm=True)
+    assert sym[0] == cases.rnafold_symbols(b_apo, n) and sym[1] == cases.rnafold_symbols(b_holo, n)
+    assert sym[1] == g["holo"]["pairing"]
+    if engine.param_provenance == "reconstructed":
+        r = g["reconstructed_par_residual"]
+        assert [k for k in range(n) if sym[0][k] != g["apo"]["pairing"][k]] == r["apo_mismatch_positions"]
+        assert dg[0, 0] == pytest.approx(r["apo_dG"], abs=5e-4) and dg[0, 1] == pytest.approx(r["holo_dG"], abs=5e-4)
+    else:
+        assert sym[0] == g["apo"]["pairing"]
+        assert abs(dg[0, 0] - g["apo"]["dG_ensemble_kcal"]) <= 0.005 and abs(dg[0, 1] - g["holo"]["dG_ensemble_kcal"]) <= 0.005

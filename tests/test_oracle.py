@@ -76,10 +76,59 @@ def test_rhf6_thresholds(oracle):
         assert apo[tri(n, i, j)] < ta and holo[tri(n, i, j)] > th
     assert oracle.macrostate_prob(s, g["active"]) < g["p_apo_active_lt"]
     assert oracle.macrostate_prob(s, g["active"], motif=cases.THEO) > g["p_holo_active_gt"]
-    # comment-level ensemble energies (RNAfold -p of the real Turner-2004 file): the reconstructed int11/21/22
-    # tables leave a small offset -- this is the "parity unpinned" gap, bounded here
-    assert dga == pytest.approx(g["comment_dG_apo"], abs=0.25)
-    assert dgh == pytest.approx(g["comment_dG_holo"], abs=0.25)
+
+
+# ---- the reference's per-position data for rhf(6) (reference tests/test_scoring.cc:52-55: two RNAfold -p strings and two ensemble
+# energies).  With the RECONSTRUCTED parameter file shipped in params/ the oracle does NOT reproduce them exactly; the tests
+# below state the true residual instead of hiding it behind a wide tolerance: they are strict xfails that a genuine
+# rna_turner2004.par (ADDAPT_B200_PAR=/path/to/rna_turner2004.par) turns into passes, and the documented residual itself is pinned.
+PAIRING = json.load(open(os.path.join(GOLD, "reference_pairing_strings.json")))
+
+
+def _reconstructed(oracle):
+    return oracle.param_provenance == "reconstructed"
+
+
+def _mismatches(a, b):
+    return [k for k in range(len(a)) if a[k] != b[k]]
+
+
+def test_rhf6_holo_pairing_string_matches_the_reference(oracle):
+    s = PAIRING["seq"]
+    _, bp = oracle.pf(s, motif=cases.THEO, bppm=True)
+    assert cases.rnafold_symbols(bp, len(s)) == PAIRING["holo"]["pairing"]
+
+
+def test_rhf6_apo_pairing_string_matches_the_reference(oracle, request):
+    if _reconstructed(oracle):
+        request.applymarker(pytest.mark.xfail(strict=True, reason="reconstructed int11/int21/int22: 7 of 102 apo symbols differ"))
+    s = PAIRING["seq"]
+    _, bp = oracle.pf(s, bppm=True)
+    got = cases.rnafold_symbols(bp, len(s))
+    bad = _mismatches(got, PAIRING["apo"]["pairing"])
+    print("apo pairing string: %d of %d symbols differ from the reference, at %s" % (len(bad), len(s), bad))
+    assert got == PAIRING["apo"]["pairing"]
+
+
+@pytest.mark.parametrize("cond", ["apo", "holo"])
+def test_rhf6_ensemble_energy_at_comment_precision(oracle, request, cond):
+    if _reconstructed(oracle):
+        request.applymarker(pytest.mark.xfail(strict=True, reason="reconstructed tables: apo -29.752 vs -29.58, holo -33.827 vs -33.82"))
+    dg = oracle.pf(PAIRING["seq"], motif=cases.THEO if cond == "holo" else None)
+    print("%s ensemble dG %.4f, reference comment %.2f, residual %+.4f kcal/mol" % (cond, dg, PAIRING[cond]["dG_ensemble_kcal"], dg - PAIRING[cond]["dG_ensemble_kcal"]))
+    assert abs(dg - PAIRING[cond]["dG_ensemble_kcal"]) <= PAIRING["comment_precision_kcal"]
+
+
+def test_rhf6_residual_of_the_reconstructed_tables_is_the_documented_one(oracle):
+    """pins the size of the gap (profiles/r2_param_sensitivity.txt attribute it to named table entries)"""
+    if not _reconstructed(oracle):
+        pytest.skip("a genuine parameter file is loaded")
+    r, s = PAIRING["reconstructed_par_residual"], PAIRING["seq"]
+    dga, apo = oracle.pf(s, bppm=True)
+    dgh, holo = oracle.pf(s, motif=cases.THEO, bppm=True)
+    assert dga == pytest.approx(r["apo_dG"], abs=5e-4) and dgh == pytest.approx(r["holo_dG"], abs=5e-4)
+    assert _mismatches(cases.rnafold_symbols(apo, len(s)), PAIRING["apo"]["pairing"]) == r["apo_mismatch_positions"]
+    assert _mismatches(cases.rnafold_symbols(holo, len(s)), PAIRING["holo"]["pairing"]) == r["holo_mismatch_positions"]
 
 
 def test_term_counts_match_survey(oracle):

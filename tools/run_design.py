@@ -28,7 +28,10 @@ def main():
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    os.environ.pop("NCCL_DEBUG", None)
+    if world > 1:      # NCCL's communicator lines are evidence, not noise: keep them, on stderr (stdout carries the JSON line)
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import addapt_b200
