@@ -103,12 +103,12 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   w.vbase = cv.take<double>((size_t)kFastVectors * w.ld);
   w.cn = cv.take<uint8_t>(w.ld);
   w.cp = cv.take<uint8_t>(w.ld);
-  w.cells = cv.take<uint16_t>(w.ld);
+  w.cells = cv.take<uint16_t>((size_t)2 * w.ld);
+  w.iscell = cv.take<uint8_t>((size_t)2 * w.ld);
   w.counter = cv.take<int>(4);
-  w.hpw = cv.take<double>(w.ld);
   w.spx = cv.take<int16_t>((size_t)3 * w.ld);
-  w.lvoff = cv.take<int>(32);
-  w.qctr = cv.take<int>(2);
+  w.lvoff = cv.take<int>(64);
+  w.qctr = cv.take<int>(4);
   w.qb = mats;
   w.qm = qm_ext ? qm_ext : mats + t4_count(n) + 1;
   w.scaleG = job.T->scale;
@@ -116,14 +116,14 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   c.has_cst = job.cst != nullptr;
   c.motif_len = job.motif ? job.motif->len : 0;
   const double mboltz = job.motif ? job.motif->boltz : 1.;
-  if (ex.tid() == 0) w.counter[2] = 0;
+  if (ex.tid() == 0) w.counter[3] = 0;
   stage_hot(ex, H, job.T);
-  for (int k = ex.tid(); k < w.ld; k += ex.nthreads()) w.vecp(10)[k] = job.T->eMLb[k];
+  for (int k = ex.tid(); k < w.ld; k += ex.nthreads()) w.vecp(kVEMLb)[k] = job.T->eMLb[k];
   load_context(ex, c, job.seq, job.cst, job.motif);   // ends with a barrier
-  if (!fast_codes(ex, c, w)) w.counter[2] = 1;
+  if (!fast_codes(ex, c, w)) w.counter[3] = 1;
   fast_special_hairpins(ex, c, job.T, w);
   ex.sync();
-  if (w.counter[2]) return false;
+  if (w.counter[3]) return false;
 #if defined(ADP_PHASE_PROFILE) && defined(__CUDA_ARCH__)
   if (blockIdx.x == 0 && threadIdx.x == 0) printf("prologue %lld cycles\n", clock64() - tp0_);
 #endif

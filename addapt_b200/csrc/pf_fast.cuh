@@ -209,9 +209,9 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
 }
 
 // The unpaired-prefix half of Qm(i,j), U(i) = sum_u eMLb^u Qm1(i+u,j), obeys U(i) = [i may stay unpaired] eMLb
-// (Qm1(i+1,j) + U(i+1)): one warp evaluates it for the whole column as a scan (two more vectors, by column parity), and the
+// (Qm1(i+1,j) + U(i+1)): one warp evaluates it for the whole column as a scan (two vectors, by column parity), and the
 // dot products of the chunk queue keep only the other half of their terms.
-constexpr int kFastVectors = 18;
+constexpr int kFastVectors = 18;      // see FastVec (inside pass) / FastVecOut (outside pass)
 
 struct FastWork {
   double* qb;      // Qb, then (outside) the outside weights: trimmed triangle
@@ -221,12 +221,12 @@ struct FastWork {
   const double* scaleG;        // pf_scale^-k (global)
   uint8_t* cn;     // [ld] code of (S[p], S[p+1])
   uint8_t* cp;     // [ld] code of (S[p], S[p-1])
-  uint16_t* cells; // [ld] rows of the current column that can pair
-  int* counter;    // [4]: 0/1 list lengths by column parity, 2 "declined" flag
-  double* hpw;     // [ld]: hairpin[u] * scale[u+2] by loop size u
+  uint16_t* cells; // [2][ld] rows of a column that can pair, by column parity
+  uint8_t* iscell; // [2][ld] whether row i of a column is in its list, by column parity
+  int* counter;    // [4]: 0..2 list lengths by column mod 3, 3 "declined" flag
   int16_t* spx;    // [3][ld]: index of the special hairpin (tri / tetra / hexa loop) closed at i, or -1
-  int* lvoff;      // [32]: byte offsets of the row candidates of the level recursion, [parity][level], for the column being prepared
-  int* qctr;       // [2]: chunk counters of the deferred work queue, by column parity
+  int* lvoff;      // [2][32]: byte offsets of the row candidates of the level recursion, [column parity][level parity][level]
+  int* qctr;       // [3]: chunk counters of the deferred work queue, by column mod 3
   double* dstate;  // NULL: every thread keeps the level sums of its anti-diagonal in registers (needs 2*R <= threads);
                    // else [2*R*kFastLevels] doubles of memory holding them (host emulation; constructs longer than threads/2)
   int ld;          // vector length (>= n + 4)
@@ -243,7 +243,8 @@ ADP_HD size_t fast_state_doubles(int n) { return (size_t)2 * fast_R(n) * kFastLe
 
 ADP_HD size_t fast_small_bytes(int n) {
   const size_t ld = (size_t)fast_ld(n);
-  return sizeof(PfHot) + 64 + ctx_bytes(n) + kFastVectors * ld * sizeof(double) + 2 * ld + 2 * ld + 64 + 16 * 12 + 34 * sizeof(int) + 32 + ld * sizeof(double) + 3 * ld * sizeof(int16_t) + 32;
+  return sizeof(PfHot) + 64 + ctx_bytes(n) + kFastVectors * ld * sizeof(double) + 2 * ld /* cn, cp */ + 2 * 2 * ld /* cells */ + 2 * ld /* iscell */ + 64 +
+         16 * 12 + (4 + 64 + 4) * sizeof(int) + 32 + 3 * ld * sizeof(int16_t) /* spx */ + 32;
 }
 ADP_HD size_t fast_matrix_doubles(int n) { return 2 * t4_count(n) + 2; }
 
@@ -302,7 +303,6 @@ ADP_HD void fast_special_hairpins(const E& ex, const SeqCtx& c, const PfTables* 
     }
     w.spx[t] = (int16_t)idx;
   }
-  for (int u = ex.tid(); u < ld; u += ex.nthreads()) w.hpw[u] = G->hairpin[u] * G->scale[u + 2];
 }
 
 template <bool kCst>
@@ -315,8 +315,8 @@ ADP_HD double fast_hairpin(const SeqCtx& c, const PfHot& H, const PfTables* G, c
   else if (u == 6) sx = w.spx[2 * w.ld + i];
   double q;
   if (sx >= 0) q = (u == 4 ? G->tetra_x : u == 6 ? G->hex_x : G->tri_x)[sx] * w.scaleG[u + 2];
-  else if (u == 3) q = type > 2 ? w.hpw[3] * H.TermAU : w.hpw[3];
-  else q = w.hpw[u] * H.mmH[mm_index(type, c.S[i + 1], c.S[j - 1])];
+  else if (u == 3) q = type > 2 ? (G->hairpin[3] * w.scaleG[5]) * H.TermAU : G->hairpin[3] * w.scaleG[5];
+  else q = (G->hairpin[u] * w.scaleG[u + 2]) * H.mmH[mm_index(type, c.S[i + 1], c.S[j - 1])];      // hairpin weight by loop size: two global loads, off the critical path
   if (is_motif_site(c, i, j)) q *= motif_boltz;   // the bound motif REPLACES the empty loop
   return q;
 }
@@ -441,17 +441,39 @@ ADP_HD int grab_chunk(const E& ex, int* ctr) {
   return ex.warp_bcast(c, 0);
 }
 
-ADP_HD int qm1_slot(int j) { const int r = j % 3; return r == 2 ? 6 : r; }     // Qm1 columns rotate through vectors 0, 1, 6
 
 // ---------------------------------------------------------------------------------------------------
 // inside pass.  Returns Z = Q(1,n) (scaled) on every thread.
-// vector roles: 0/1/6 Qm1 columns (by column mod 3), 2 and 7 exterior terms per row by column parity, 3 xA (Qb * terminal
-// factor, column j-1), 4/5 x1n (Qb * 1xn mismatch, by column parity), 8 hairpin weight / 13 multiloop stem factor / 14 exterior
-// stem factor * q1 of the cells of the column being prepared, 9 q1, 10 eMLb powers, 11/12 generic-loop sums per level parity.
+//
+// ONE barrier per column (round 2; round 1 had two).  Everything a thread does between barrier j-1 and barrier j ("phase j")
+// reads only what was complete at barrier j-1, so the pieces of a phase may run in any order and on any warp:
+//   cells(j)        Qb(i,j) of the listed cells, a lane group per cell; the group's first lane also writes the cell's share of
+//                   Qm1(.,j) and of the premultiplied column vectors xA / x1n of column j
+//   levels(j+1)     level sums of the generic loops of the NEXT column (reads columns <= j-2); thread-bound (registers)
+//   list(j+1)       the cells of the next column and their hairpin weights
+//   rest(j)         rows of column j that cannot pair: unpaired extension of Qm1, zeros in xA / x1n
+//   q1(j-1)         exterior prefix from the finished column of Qb (one warp)
+//   scan(j-1)       unpaired-prefix half of Qm(., j-1) from the finished Qm1 column (one warp)
+//   drain(j-2)      the other half of Qm(., j-2), from a queue of warp-sized chunks: whoever is idle takes the next one
+// Cells are assigned from thread 0 upwards; the list / rest rows, the two single-warp jobs and (being last in program order)
+// the chunk queue fall to the warps that hold no cells, so the phase ends when the busiest warp does.  Buffers that are
+// written for the next column while the current one is read are double-buffered by column parity, those with a third
+// live column (Qm1, x1n, the list and queue counters) rotate mod 3.
+enum FastVec : int {
+  kVQ1 = 0, kVEMLb = 1,                     // shared with the outside pass: exterior prefix q1, eMLb powers
+  kVQm1 = 2,                                // +3: Qm1 columns by column mod 3
+  kVXA = 5,                                 // +2: Qb * terminal factor (bulge filter), by column parity
+  kVX1n = 7,                                // +3: Qb * 1xn mismatch ratio, by column mod 3
+  kVHp = 10,                                // +2: hairpin weight of the listed cells, by column parity
+  kVGen0 = 12, kVGen1 = 14,                 // +2 each: generic-loop sums per level parity, by column parity
+  kVU = 16                                  // +2: unpaired-prefix half of Qm by column parity
+};
+
 template <bool kCst, class E>
 ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const PfTables* G, double motif_boltz, FastWork& w) {
   const int n = c.n, nt = ex.nthreads(), tid = ex.tid(), ld = w.ld, R = w.R;
   const int nt_lg = ilog2_floor((unsigned)nt), warp_lg = ilog2_floor((unsigned)E::kWarp);
+  const int nwarp = nt >> warp_lg;
   const bool mem_state = E::kSerial || w.dstate != nullptr;   // level sums in memory: host emulation, or more anti-diagonals than threads
   const int half = mem_state ? R : (nt >> 1);        // anti-diagonal slots per level parity (>= R)
   const int ntri = (int)t4_count(n);
@@ -460,23 +482,19 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
   const uint8_t* const cn = w.cn;
   const uint8_t* const cp = w.cp;
   for (int k = tid; k < ntri; k += nt) { qb[k] = 0.; qm[k] = 0.; }
-  for (int k = tid; k < 15 * ld; k += nt)
-    if (k < 10 * ld || k >= 11 * ld) w.vbase[k] = 0.;
-  double* const q1 = w.vecp(9);
-  const double* const eMLbS = w.vecp(10);
-  double* const xA = w.vecp(3);
-  double* const gen0 = w.vecp(11);
-  double* const gen1 = w.vecp(12);
-  double* const hp = w.vecp(8);
-  double* const smv = w.vecp(13);
-  double* const sev = w.vecp(14);
+  for (int k = tid; k < kFastVectors * ld; k += nt)
+    if (k < kVEMLb * ld || k >= (kVEMLb + 1) * ld) w.vbase[k] = 0.;
+  double* const q1 = w.vecp(kVQ1);
+  const double* const eMLbS = w.vecp(kVEMLb);
   double d[kFastLevels];     // level sums of this thread's anti-diagonal (registers)
   const double* const zp = &H.pad;   // an always-zero word for levels that are off
   ADP_LEVEL_ZERO()
   ADP_PROF_DECL
   if (mem_state)
     for (int k = tid; k < 2 * R * kFastLevels; k += nt) w.dstate[k] = 0.;
-  if (tid == 0) { w.counter[0] = 0; w.counter[1] = 0; w.qctr[0] = 0; w.qctr[1] = 0; }
+  if (tid == 0)
+    for (int k = 0; k < 3; k++) { w.counter[k] = 0; w.qctr[k] = 0; }
+  for (int t = tid; t < 64; t += nt) w.lvoff[t] = 0;
   ex.sync();
   const double s1 = H.scale1, eb1 = H.eMLb1;
   if (tid == 0) {
@@ -485,17 +503,15 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     for (int j = 1; j <= 4 && j <= n; j++) q1[j] = (!kCst || can_unpair(c, j)) ? q1[j - 1] * s1 : 0.;
   }
 
-  // everything column `jn` needs before its cells can be evaluated, and that does not depend on column jn-1:
-  // level sums of the generic loops, the unpaired-extension part of Qm1, the list of cells and their sequence-only factors
-  auto prepare_column = [&](int jn) {
+  // level sums of the generic interior loops of column jn (reads Qb columns <= jn-3)
+  auto levels = [&](int jn) {
     const int nr = jn - 4;
-    const bool cuj = !kCst || can_unpair(c, jn);
     const bool cuj1 = !kCst || can_unpair(c, jn - 1);
     const int upl_j1 = kCst ? (int)c.upl[jn - 1] : 1000;
     const double* col3 = qb + (((jn - 7) * (jn - 8)) >> 1) - 2;   // Qb*FI(k, jn-3) = col3[k + 1]
-    const double* qm1_prev = w.vecp(qm1_slot(jn - 1));
-    double* qm1_cur = w.vecp(qm1_slot(jn));
-    int* counter = w.counter + (jn & 1);
+    double* const gen0 = w.vecp(kVGen0 + (jn & 1));
+    double* const gen1 = w.vecp(kVGen1 + (jn & 1));
+    const int* const lvo = w.lvoff + ((jn & 1) << 5);
     for (int task = tid; task < 2 * half; task += nt) {
       const int par = task >= half ? 1 : 0;          // warp-uniform: the two parities are separate code paths
       int key = task - par * half;
@@ -523,7 +539,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
           const char* qrow = reinterpret_cast<const char*>(qb + i + 2);   // Qb*FI(i+3, l) = qrow[(l-4)(l-5)/2], l = jn+1-S: offset from the table
           const double* fcn = ADP_FC.nin + (par << 4);
           const double* fci = ADP_FC.ip + (par << 4);
-          ADP_LEVEL_OFFSETS(w.lvoff + (par << 4))
+          ADP_LEVEL_OFFSETS(lvo + (par << 4))
 #define ADP_A1(Q) reinterpret_cast<const double*>(qrow + lo[Q])
 #define ADP_C1(Q) (!kCst || (ok1 && 2 * (Q) <= lim1))
 #define ADP_A2(Q) (xi + 2 * (Q))
@@ -541,27 +557,67 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       if (mem_state)
         for (int q = 0; q < kFastLevels; q++) w.dstate[(size_t)task * kFastLevels + q] = d[q];
     }
-    ADP_TICK(4)
-    double* ext_n = w.vecp((jn & 1) ? 7 : 2);      // exterior terms by ROW (summed in row order: results do not depend on list order)
+  };
+
+  // the cells of column jn and their hairpin weights, a thread per row, rows handed out from the last thread downwards (the
+  // first threads hold the cells of the current column)
+  auto list_rows = [&](int jn) {
+    const int nr = jn - 4;
+    double* const hp = w.vecp(kVHp + (jn & 1));
+    uint16_t* const cells = w.cells + (jn & 1) * ld;
+    uint8_t* const iscell = w.iscell + (jn & 1) * ld;
+    int* const counter = w.counter + (jn % 3);
     ADP_NOUNROLL
-    for (int r = tid; r < nr; r += nt) {
+    for (int r = nt - 1 - tid; r < nr; r += nt) {
       const int i = r + 1;
-      qm1_cur[i] = cuj ? qm1_prev[i] * eb1 : 0.;
-      ext_n[i] = 0.;
       const int type = kCst ? allowed_type(c, i, jn) : pair_type(c.S[i], c.S[jn]);
+      iscell[i] = type != 0;
       if (type != 0) {
-        w.cells[ex.atomic_inc(counter)] = (uint16_t)i;
-        // what the cell needs from the sequence alone is computed here, by a thread per row, instead of by one lane of the cell's group
+        cells[ex.atomic_inc(counter)] = (uint16_t)i;
 #if defined(ADP_X_NOHP)
-        hp[i] = 0.01; smv[i] = 0.5; sev[i] = 0.5 * q1[i - 1];
+        hp[i] = 0.01;
 #else
         hp[i] = fast_hairpin<kCst>(c, H, G, w, motif_boltz, i, jn, type);
-        smv[i] = fast_stem_ml(c, H, w, type, i, jn);
-        sev[i] = fast_stem_ext(c, H, type, i, jn) * q1[i - 1];
 #endif
       }
     }
-    ADP_TICK(5)
+  };
+
+  // rows of column j that hold no cell
+  auto rest_rows = [&](int j) {
+    const int nr = j - 4;
+    const bool cuj = !kCst || can_unpair(c, j);
+    const double* const qm1_prev = w.vecp(kVQm1 + (j - 1) % 3);
+    double* const qm1_cur = w.vecp(kVQm1 + j % 3);
+    double* const xA = w.vecp(kVXA + (j & 1));
+    double* const x1n = w.vecp(kVX1n + j % 3);
+    const uint8_t* const iscell = w.iscell + (j & 1) * ld;
+    ADP_NOUNROLL
+    for (int r = nt - 1 - tid; r < nr; r += nt) {
+      const int i = r + 1;
+      if (iscell[i]) continue;
+      qm1_cur[i] = cuj ? qm1_prev[i] * eb1 : 0.;
+      xA[i] = 0.;
+      x1n[i] = 0.;
+    }
+  };
+
+  // exterior prefix of the finished column jq: q1[jq] = [jq unpaired] q1[jq-1] scale + sum_i q1[i-1] Qb(i,jq) stem(i,jq), by one
+  // warp straight from the column of Qb (summed in row order: the result does not depend on the list order)
+  auto q1_task = [&](int jq) {
+    const double* const col = qb + t4(1, jq) - 1;        // Qb (premultiplied) (i, jq) = col[i]
+    const int cnq = cn[jq] << 4, sq = c.S[jq];
+    double e = 0.;
+    ADP_NOUNROLL
+    for (int i = 1 + ex.lane(); i <= jq - 4; i += E::kWarp) {
+      const double v = col[i];
+      if (v != 0.) {
+        const double plain = (i > 1 && jq < n) ? v * H.RI[cnq | cp[i]] : v;      // back to the plain Qb(i,jq)
+        e += plain * fast_stem_ext(c, H, pair_type(c.S[i], sq), i, jq) * q1[i - 1];
+      }
+    }
+    e = ex.warp_sum(e);
+    if (ex.lane() == 0) q1[jq] = ((!kCst || can_unpair(c, jq)) ? q1[jq - 1] * s1 : 0.) + e;
   };
 
   // U(., jq) for the finished Qm1 column jq, by one warp: every lane folds a block of rows into an affine map, a suffix scan
@@ -569,8 +625,8 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
   auto scan_unpaired = [&](int jq) {
     const int nrq = jq - 4;
     if (nrq < 1) return;
-    double* Uv = w.vecp(16 + (jq & 1));
-    const double* x = w.vecp(qm1_slot(jq));
+    double* Uv = w.vecp(kVU + (jq & 1));
+    const double* x = w.vecp(kVQm1 + jq % 3);
     const int lane = ex.lane();
     const int B = (nrq + E::kWarp - 1) / E::kWarp;
     const int lo = lane * B + 1;
@@ -598,8 +654,8 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     }
   };
 
-  // Qm(., jq) from the finished Qm1 column jq: row pairs (rows paired so that every pair sums the same number of terms), a few
-  // lanes per pair, a warp-sized chunk of pairs at a time from the queue.  Qm(., jq) is first read by column jq + 5.
+  // Qm(., jq) from the finished Qm1 column jq and its scan: row pairs (rows paired so that every pair sums the same number of
+  // terms), a few lanes per pair, a warp-sized chunk of pairs at a time from the queue.  Qm(., jq) is first read by column jq + 5.
   auto drain_qm = [&](int jq) {
     const int nrq = jq - 4;
     if (nrq < 1) return;
@@ -607,8 +663,9 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     const int lgc = E::kSerial ? 0 : (nrq >= 24 ? 2 : 3);
     const int Gc = 1 << lgc, per = E::kWarp >> lgc, subC = ex.lane() & (Gc - 1);
     const int nchunk = (npair + per - 1) / per;
-    const double* qm1q = w.vecp(qm1_slot(jq));
-    int* ctr = w.qctr + ((jq + 1) & 1);
+    const double* qm1q = w.vecp(kVQm1 + jq % 3);
+    const double* Uq = w.vecp(kVU + (jq & 1));
+    int* ctr = w.qctr + (jq % 3);
     for (;;) {
       const int ch = grab_chunk(ex, ctr);
       if (ch >= nchunk) break;
@@ -616,7 +673,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       const bool valid = slot < npair;
       const int iA = slot + 1, iB = nrq - slot;       // iA <= iB; equal for the middle row of an odd count
       double tA = 0., tB = 0.;
-      const double* Uq = w.vecp(16 + (jq & 1));
       if (valid) {      // run = 0: the unpaired-prefix terms come from the scan
         tA = qm_row_terms(qm, qm1q, eMLbS, iA, nrq, 0, subC, Gc);
         if (iB > iA) tB = qm_row_terms(qm, qm1q, eMLbS, iB, nrq, 0, subC, Gc);
@@ -629,38 +685,42 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     }
   };
 
-  for (int t = tid; t < 32; t += nt) w.lvoff[t] = 0;
   ex.sync();
   // j = 4 is a warm-up turn without cells: it only prepares column 5 (one call site keeps the code small)
   for (int j = 4; j <= n; j++) {
-    const int nr = j - 4;                       // rows 1 .. nr
     const bool cuj = !kCst || can_unpair(c, j);
-    const double* qm1_prev = w.vecp(qm1_slot(j - 1));
-    double* qm1_cur = w.vecp(qm1_slot(j));
-    double* ext = w.vecp((j & 1) ? 7 : 2);
-    const int m = w.counter[j & 1];
-    // ---- interval 1: Qb(i,j) for the listed cells, a lane group per cell; then deferred work
-    {
-      if (tid == 0) { w.counter[(j + 1) & 1] = 0; w.qctr[(j + 1) & 1] = 0; }
-      ADP_NOUNROLL
-      for (int t = tid; t < 32; t += nt) {
-        // byte offsets of the row candidates of the level recursion of column j+1: level S reads Qb*FI(i+3, j+2-S)
-        const int S = 4 + (t >> 4) + 2 * (t & 15);
-        const int l = j + 2 - S;
-        w.lvoff[t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(double);
-      }
+    const double* qm1_prev = w.vecp(kVQm1 + (j - 1) % 3);
+    double* qm1_cur = w.vecp(kVQm1 + j % 3);
+    const int m = w.counter[j % 3];
+    if (tid == 0) { w.counter[(j + 2) % 3] = 0; w.qctr[(j + 2) % 3] = 0; }      // the slots of phase j+2 (nobody reads them in this phase)
+    ADP_NOUNROLL
+    for (int t = tid; t < 32; t += nt) {
+      // byte offsets of the row candidates of the level recursion of column j+2 (evaluated in phase j+1): level S reads Qb*FI(i+3, j+3-S)
+      const int S = 4 + (t >> 4) + 2 * (t & 15);
+      const int l = j + 3 - S;
+      w.lvoff[((j & 1) << 5) + t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(double);
+    }
+    // ---- cells(j): Qb(i,j) for the listed cells, a lane group per cell
+    if (m > 0) {
+      const double* const hp = w.vecp(kVHp + (j & 1));
+      const double* const gen0 = w.vecp(kVGen0 + (j & 1));
+      const double* const gen1 = w.vecp(kVGen1 + (j & 1));
+      const double* const xA_rd = w.vecp(kVXA + ((j - 1) & 1));      // column j-1
+      const double* const x1n_rd = w.vecp(kVX1n + (j - 2) % 3);      // column j-2
+      double* const xA_wr = w.vecp(kVXA + (j & 1));
+      double* const x1n_wr = w.vecp(kVX1n + j % 3);
+      const uint16_t* const cells = w.cells + (j & 1) * ld;
       const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
-      const double* x1n_rd = w.vecp(4 + (j & 1));     // column j-2
       const int upl_j1 = kCst ? (int)c.upl[j - 1] : 1000;
-      const int sj = c.S[j], sj1 = c.S[j - 1], cpj = cp[j];
+      const int sj = c.S[j], cpj = cp[j], cnj = cn[j] << 4;
       for (int slot0 = 0; slot0 < m; slot0 += slots) {
         const int slot = slot0 + (tid >> lg);
         const bool valid = slot < m;
-        const int i = valid ? w.cells[slot] : 1;
+        const int i = valid ? cells[slot] : 1;
         double acc = 0.;
         if (valid) {
-          const int si = c.S[i], si1 = c.S[i + 1];
+          const int si = c.S[i];
           const int type = pair_type(si, sj);
           const int codeij = (cn[i] << 4) | cpj;
           const int room = j - i - 6;                 // u1 + u2 <= room keeps the inner pair >= 4 apart
@@ -672,8 +732,8 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
           if (sub == 0) other = hp[i] + H.FI[codeij] * (gen0[i] + gen1[i]);
           ADP_TICK(8)
           if (room >= 0) {
-            // corner candidates through the full tables, one per lane and round.  Software-pipelined and kept rolled (code size):
-            // the table load of a round is issued in that round and consumed in the next, the last one after the filters below.
+            // corner candidates through the code-indexed table, one per lane and round.  Software-pipelined and kept rolled (code
+            // size): the table load of a round is issued in that round and consumed in the next, the last one after the filters below.
 #if !defined(ADP_X_NOCORNER)
             if (sub == Gs - 1) {
               // the stack (u1 = u2 = 0) as straight-line code on the group's last lane: both types come from the cell's own codes
@@ -718,7 +778,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               if (u2cap < 1) hi31 = -1;
               const int hmax = hiB3 > hiB5 ? hiB3 : hiB5;
               const int cpk1 = cp[i + 1], cpk2 = cp[i + 2];
-              const double* xa = xA + i + 1;
+              const double* xa = xA_rd + i + 1;
               const double* xn = x1n_rd + i + 1;
               for (int u = 2 + sub; u <= hmax; u += Gs) {
                 const int l = j - 1 - u;                       // >= i + 5: (i+1,l) is a cell; (i+2,l) is one unless u = room
@@ -757,47 +817,39 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         acc = ex.group_sum_rt(acc, Gs);
         ADP_TICK(12)
         if (valid && sub == 0) {
-          qb[t4(i, j)] = (i > 1 && j < n) ? acc * H.FI[(cn[j] << 4) | cp[i]] : acc;     // stored premultiplied
-          qm1_cur[i] += acc * smv[i];
-          ext[i] = acc * sev[i];
+          const int code = cnj | cp[i];
+          const double pre = (i > 1 && j < n) ? acc * H.FI[code] : acc;     // stored premultiplied; rows / columns at the sequence
+          qb[t4(i, j)] = pre;                                               // ends are never read back by the loop terms
+          xA_wr[i] = pre * H.RB[code];
+          x1n_wr[i] = pre * H.R1[code];
+          qm1_cur[i] = (cuj ? qm1_prev[i] * eb1 : 0.) + acc * fast_stem_ml(c, H, w, pair_type(c.S[i], sj), i, j);
         }
         ADP_TICK(13)
       }
-      ADP_TICK(0)
     }
-    ex.sync();
-    ADP_TICK(2)
-    // ---- interval 2: premultiplied vectors of the new column; exterior prefix; preparation of column j+1; what is left
-    //      of the deferred work
-    {
-      if (ex.warp() == (nt >> warp_lg) - 1) scan_unpaired(j);
-      double* x1n_wr = w.vecp(4 + (j & 1));
-      const int cnj = cn[j] << 4;
-      ADP_NOUNROLL
-      for (int r = tid; r < nr; r += nt) {
-        const int i = r + 1;
-        const double v = qb[t4(i, j)];                  // Qb * FI; rows / columns at the sequence ends are never read back
-        const int code = cnj | cp[i];
-        xA[i] = v * H.RB[code];
-        x1n_wr[i] = v * H.R1[code];
-      }
-      if (ex.warp() == 0) {
-        double e = 0.;
-        ADP_NOUNROLL
-        for (int s = 1 + ex.lane(); s <= nr; s += E::kWarp) e += ext[s];
-        e = ex.warp_sum(e);
-        if (ex.lane() == 0) q1[j] = (cuj ? q1[j - 1] * s1 : 0.) + e;
-      }
-      ADP_TICK(3)
-      if (j < n) prepare_column(j + 1);
+    ADP_TICK(0)
+    // ---- everything else of the phase
+    if (j < n) levels(j + 1);
+    ADP_TICK(4)
+    if (j < n) list_rows(j + 1);
+    if (j >= 5) rest_rows(j);
+    ADP_TICK(5)
+    if (j >= 6 && ex.warp() == nwarp - 1) q1_task(j - 1);
+    if (j >= 6 && ex.warp() == (nwarp > 1 ? nwarp - 2 : 0)) scan_unpaired(j - 1);
+    ADP_TICK(3)
 #if !defined(ADP_X_NOQM)
-      drain_qm(j - 1);
+    if (j >= 7) drain_qm(j - 2);
 #endif
-      ADP_TICK(6)
-    }
+    ADP_TICK(6)
     ex.sync();
     ADP_TICK(7)
   }
+  // epilogue: the exterior prefix of the last column and Qm(., n-1), which the outside pass reads
+  if (n >= 5 && ex.warp() == nwarp - 1) q1_task(n);
+#if !defined(ADP_X_NOQM)
+  if (n >= 6) drain_qm(n - 1);
+#endif
+  ex.sync();
   ADP_PROF_REPORT("inside ")
   return q1[n];
 }
@@ -805,10 +857,20 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
 // ---------------------------------------------------------------------------------------------------
 // outside pass.  Overwrites Qb column by column (l = n .. 5) with the outside weights; the probabilities of a
 // column go to `bppm` / the pair queries as soon as the column is complete.
-// vector roles: 0 A(i,l) (multiloop carrier with >= 1 stem right of l), 1 B(i,l) (nothing right of l),
-// 2 and 6 P(.,l) of the finished column by parity, 3 xA (Pout * terminal factor, column l+1), 4/5 x1n (by column
-// parity), 8 exterior stem factor of the cells of the column being prepared, 9 q1, 10 eMLb powers, 11/12 generic sums, 13 qln,
-// 14 exterior-suffix accumulators, 15 bound-motif probabilities per site.
+// vector roles: see FastVecOut.
+enum FastVecOut : int {
+  kOA = 2,                                  // A(i,l): multiloop carrier with >= 1 stem right of l
+  kOB = 3,                                  // B(i,l): nothing right of l
+  kOP = 4,                                  // +2: P(.,l) of the finished column, by column parity
+  kOXA = 6,                                 // Pout * terminal factor, column l+1
+  kOX1n = 7,                                // +2: Pout * 1xn mismatch ratio, by column parity
+  kOSx = 9,                                 // exterior stem factor of the cells of the column being prepared
+  kOGen0 = 10, kOGen1 = 11,                 // generic-loop sums per level parity
+  kOQln = 12,                               // exterior suffix Q(l,n)
+  kOAcc = 13,                               // exterior-suffix accumulators
+  kOPm = 14                                 // bound-motif probabilities per site
+};
+
 struct FastOut {
   double* bppm;          // NULL or n(n+1)/2 doubles, row-major upper triangle incl. diagonal, 0-based
   int n_query;
@@ -833,18 +895,18 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   const uint8_t* const cn = w.cn;
   const uint8_t* const cp = w.cp;
   for (int k = tid; k < kFastVectors * ld; k += nt)
-    if (k < 9 * ld || k >= 11 * ld) w.vbase[k] = 0.;
-  double* const vA = w.vecp(0);
-  double* const vB = w.vecp(1);
-  double* const sxv = w.vecp(8);
-  double* const xA = w.vecp(3);
-  const double* const q1 = w.vecp(9);
-  const double* const eMLbS = w.vecp(10);
-  double* const gen0 = w.vecp(11);
-  double* const gen1 = w.vecp(12);
-  double* const qln = w.vecp(13);
-  double* const accq = w.vecp(14);
-  double* const pm = w.vecp(15);
+    if (k >= 2 * ld) w.vbase[k] = 0.;      // everything but q1 and the eMLb powers
+  double* const vA = w.vecp(kOA);
+  double* const vB = w.vecp(kOB);
+  double* const sxv = w.vecp(kOSx);
+  double* const xA = w.vecp(kOXA);
+  const double* const q1 = w.vecp(kVQ1);
+  const double* const eMLbS = w.vecp(kVEMLb);
+  double* const gen0 = w.vecp(kOGen0);
+  double* const gen1 = w.vecp(kOGen1);
+  double* const qln = w.vecp(kOQln);
+  double* const accq = w.vecp(kOAcc);
+  double* const pm = w.vecp(kOPm);
   if (out.bppm) {
     const size_t ntot = (size_t)n * (n + 1) / 2;
     for (size_t k = tid; k < ntot; k += nt) out.bppm[k] = 0.;
@@ -961,7 +1023,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     }
     ADP_TICK(4)
     // (d) the cells of this column that carry weight; the column's probability vector starts at zero
-    double* pcol = w.vecp((ln & 1) ? 6 : 2);
+    double* pcol = w.vecp(kOP + (ln & 1));
     int* counter = w.counter + (ln & 1);
     ADP_NOUNROLL
     for (int r = tid; r < nr; r += nt) {
@@ -979,7 +1041,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   // l = n+1 is a warm-up turn without cells: it only prepares column n (one call site keeps the code small)
   for (int l = n + 1; l >= kTurn + 2; l--) {
     const int nr = l <= n ? l - 4 : 0;          // rows k = 1 .. nr
-    double* pcol = w.vecp((l & 1) ? 6 : 2);
+    double* pcol = w.vecp(kOP + (l & 1));
     const int m = l <= n ? w.counter[l & 1] : 0;
     // ---- interval 1: outside weight of every listed pair (k,l); then deferred work
     {
@@ -993,7 +1055,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       }
       const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
-      const double* x1n_rd = w.vecp(4 + (l & 1));        // column l+2
+      const double* x1n_rd = w.vecp(kOX1n + (l & 1));        // column l+2
       const int upr_l1 = kCst ? (int)c.upr[l + 1] : n - l;
       const int sl = c.S[l], sq1 = c.S[l + 1], cnl = cn[l] << 4;
       int u2cap = upr_l1;                         // also keeps j = l+1+u2 <= n when unconstrained
@@ -1113,7 +1175,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     ADP_TICK(2)
     // ---- interval 2: premultiplied vectors of the finished column; results; preparation of column l-1
     {
-      double* x1n_wr = w.vecp(4 + (l & 1));
+      double* x1n_wr = w.vecp(kOX1n + (l & 1));
       const int cpl = cp[l];
       ADP_NOUNROLL
       for (int r = tid; r < nr + 3; r += nt) {
