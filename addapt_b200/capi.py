@@ -24,12 +24,17 @@ class _Motif(C.Structure):
     _fields_ = [("seq", C.c_char_p), ("fold", C.c_char_p), ("kd_uM", C.c_double)]
 
 
+class _BpTerm(C.Structure):
+    _fields_ = [("kind", C.c_int), ("cond", C.c_int), ("favorable", C.c_int), ("weight", C.c_double), ("i", C.c_int), ("j", C.c_int),
+                ("n_pos", C.c_int), ("pos", C.POINTER(C.c_int))]
+
+
 class _Problem(C.Structure):
     _fields_ = [("n", C.c_int), ("init_seq", C.c_char_p), ("n_macro", C.c_int), ("macro_cst", C.POINTER(C.c_char_p)),
                 ("n_terms", C.c_int), ("term_macro", C.POINTER(C.c_int)), ("term_cond", C.POINTER(C.c_int)),
                 ("term_favorable", C.POINTER(C.c_int)), ("term_weight", C.POINTER(C.c_double)), ("motif", _Motif),
                 ("n_ctx", C.c_int), ("ctx_before", C.POINTER(C.c_char_p)), ("ctx_after", C.POINTER(C.c_char_p)),
-                ("float_dg", C.c_int)]
+                ("float_dg", C.c_int), ("n_bp_terms", C.c_int), ("bp_terms", C.POINTER(_BpTerm))]
 
 
 def _b(s):
@@ -41,12 +46,14 @@ class Problem:
 
     seq: mixed-case sequence (upper = mutable); macrostates: {name: constraint}; terms: list of
     (macrostate name, 'apo'|'holo', favorable bool, weight); motif: (seq, fold, kd_uM) or None;
-    contexts: list of (before, after).
+    contexts: list of (before, after); bp_terms: base-pair-probability terms, each ("pair", 'apo'|'holo', favorable, weight, i, j)
+    or ("density", 'apo'|'holo', favorable, weight, [positions]) with 0-based positions of the raw device (include/addapt_b200.h).
+    Term values come back as [context][macrostate terms..., bp terms...].
     """
 
-    def __init__(self, seq, macrostates, terms, motif=None, contexts=None, float_dg=False):
+    def __init__(self, seq, macrostates, terms, motif=None, contexts=None, float_dg=False, bp_terms=None):
         self.seq, self.macrostates, self.terms, self.motif = seq, dict(macrostates), list(terms), motif
-        self.contexts, self.float_dg = list(contexts or []), bool(float_dg)
+        self.contexts, self.float_dg, self.bp_terms = list(contexts or []), bool(float_dg), list(bp_terms or [])
         names = list(self.macrostates)
         k = self._keep = {}
         k["macro"] = (C.c_char_p * max(len(names), 1))(*([_b(self.macrostates[m]) for m in names] or [b""]))
@@ -59,13 +66,24 @@ class Problem:
         k["cb"] = (C.c_char_p * max(len(ctx), 1))(*([_b(c[0]) for c in ctx] or [b""]))
         k["ca"] = (C.c_char_p * max(len(ctx), 1))(*([_b(c[1]) for c in ctx] or [b""]))
         m = _Motif(_b(motif[0]), _b(motif[1]), float(motif[2])) if motif else _Motif(None, None, 0.0)
+        bp = (_BpTerm * max(len(self.bp_terms), 1))()
+        k["bp"], k["bp_pos"] = bp, []
+        for q, t in enumerate(self.bp_terms):
+            kind, cond, fav, w = t[0], t[1], t[2], t[3]
+            bp[q].kind, bp[q].cond, bp[q].favorable, bp[q].weight = (0 if kind == "pair" else 1), (1 if cond == "holo" else 0), int(bool(fav)), float(w)
+            if kind == "pair":
+                bp[q].i, bp[q].j, bp[q].n_pos, bp[q].pos = int(t[4]), int(t[5]), 0, None
+            else:
+                arr = (C.c_int * len(t[4]))(*[int(x) for x in t[4]])
+                k["bp_pos"].append(arr)
+                bp[q].i, bp[q].j, bp[q].n_pos, bp[q].pos = 0, 0, len(t[4]), arr
         self.c = _Problem(len(seq), _b(seq), len(names), k["macro"], len(T), k["tm"], k["tc"], k["tf"], k["tw"], m,
-                          len(ctx), k["cb"], k["ca"], int(self.float_dg))
+                          len(ctx), k["cb"], k["ca"], int(self.float_dg), len(self.bp_terms), bp)
         self.n = len(seq)
-        self.n_term_values = max(len(ctx), 1) * len(T)
+        self.n_term_values = max(len(ctx), 1) * (len(T) + len(self.bp_terms))
 
     def as_oracle_dict(self):
-        return dict(seq=self.seq, macrostates=self.macrostates, terms=self.terms, motif=self.motif, contexts=self.contexts)
+        return dict(seq=self.seq, macrostates=self.macrostates, terms=self.terms, motif=self.motif, contexts=self.contexts, bp_terms=self.bp_terms)
 
 
 def library_path():
@@ -97,10 +115,11 @@ def load_library():
     L.adp_engine_set_general_only.argtypes = [vp, ci]
     L.adp_kT_kcal.argtypes = [vp]
     L.adp_kT_kcal.restype = cd
-    L.adp_param_provenance.argtypes = [vp]
-    L.adp_param_provenance.restype = cs
-    L.adp_param_file.argtypes = [vp]
-    L.adp_param_file.restype = cs
+    if hasattr(L, "adp_param_provenance"):        # absent only from older tuning builds selected with ADDAPT_B200_LIB
+        L.adp_param_provenance.argtypes = [vp]
+        L.adp_param_provenance.restype = cs
+        L.adp_param_file.argtypes = [vp]
+        L.adp_param_file.restype = cs
     L.adp_device_count.restype = ci
     L.adp_launch_count.argtypes = [vp]
     L.adp_launch_count.restype = C.c_uint64
@@ -112,6 +131,10 @@ def load_library():
     L.adp_score_batch.argtypes = [vp, C.POINTER(_Problem), ci, vp, vp, vp]
     L.adp_mc_run.argtypes = [vp, C.POINTER(_Problem), ci, C.c_uint64, C.c_uint64, ci, ci, C.POINTER(cd), vp, vp, vp, vp, vp, vp]
     L.adp_measure_dfma_rate.argtypes = [vp, C.POINTER(cd)]
+    if hasattr(L, "adp_mc_run_trace"):            # absent only from older tuning builds selected with ADDAPT_B200_LIB
+        L.adp_mc_trace_width.argtypes = [C.POINTER(_Problem)]
+        L.adp_mc_run_trace.argtypes = [vp, C.POINTER(_Problem), ci, C.c_uint64, C.c_uint64, ci, ci, C.POINTER(cd), vp, vp, vp, vp, vp, vp, ci, vp, vp]
+        L.adp_mutate_batch.argtypes = [vp, C.POINTER(_Problem), ci, vp, vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -159,8 +182,9 @@ class Engine:
             raise EngineError("adp_engine_create failed (%d): %s" % (rc, (self.lib.adp_last_error(None) or b"").decode()))
         self.h = h
         self.kT = self.lib.adp_kT_kcal(self.h)
-        self.param_provenance = (self.lib.adp_param_provenance(self.h) or b"").decode()
-        self.param_file = (self.lib.adp_param_file(self.h) or b"").decode()
+        has = hasattr(self.lib, "adp_param_provenance")
+        self.param_provenance = (self.lib.adp_param_provenance(self.h) or b"").decode() if has else "unknown"
+        self.param_file = (self.lib.adp_param_file(self.h) or b"").decode() if has else par_file
 
     def close(self):
         if getattr(self, "h", None):
@@ -273,7 +297,20 @@ class Engine:
     def score_raw(self, problem, B, seqs, score, terms=None):
         self._check(self.lib.adp_score_batch(self.h, C.byref(problem.c), B, _ptr(seqs), _ptr(score), _ptr(terms)))
 
-    def mc_run(self, problem, n_traj, seed, n_steps, thermostat=("annealing", 5.0, 0.0, 300), traj_id0=0):
+    def mutate(self, problem, seqs, positions, nucleotides):
+        """≙ mutate_recursively for every (sequence, position, nucleotide) triple, applied on the device; returns the mutated
+        sequences and the can_be_freely_mutated flag of every position (reference src/sampling.cc:177-193, 205-282)."""
+        a = seqs_to_array(seqs)
+        B, n = a.shape
+        assert n == problem.n and len(positions) == B and len(nucleotides) == B
+        pos = np.ascontiguousarray(positions, dtype=np.int32)
+        nts = np.frombuffer("".join(nucleotides).encode(), dtype=np.uint8).copy()
+        out = np.zeros((B, n), dtype=np.uint8)
+        free = np.zeros(B, dtype=np.int32)
+        self._check(self.lib.adp_mutate_batch(self.h, C.byref(problem.c), B, _ptr(a), _ptr(pos), _ptr(nts), _ptr(out), _ptr(free)))
+        return [bytes(r).decode() for r in out], [bool(x) for x in free]
+
+    def mc_run(self, problem, n_traj, seed, n_steps, thermostat=("annealing", 5.0, 0.0, 300), traj_id0=0, trace_interval=0):
         n = problem.n
         if thermostat[0] == "fixed":
             kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
@@ -286,10 +323,18 @@ class Engine:
         fsc, bsc = np.zeros(n_traj), np.zeros(n_traj)
         bst = np.zeros(n_traj, dtype=np.int32)
         oc = np.zeros((n_traj, 4), dtype=np.uint32)
-        self._check(self.lib.adp_mc_run(self.h, C.byref(problem.c), n_traj, seed, traj_id0, n_steps, kind, ta,
-                                        _ptr(fs), _ptr(fsc), _ptr(bs), _ptr(bsc), _ptr(bst), _ptr(oc)))
-        return dict(final_seq=[bytes(r).decode() for r in fs], final_score=fsc, best_seq=[bytes(r).decode() for r in bs],
-                    best_score=bsc, best_step=bst, outcomes=oc)
+        tv = tq = None
+        if trace_interval > 0 and n_steps > 0:
+            cap, width = (n_steps + trace_interval - 1) // trace_interval, self.lib.adp_mc_trace_width(C.byref(problem.c))
+            tv = np.zeros((n_traj, cap, width))
+            tq = np.zeros((n_traj, cap, 2, n), dtype=np.uint8)
+        self._check(self.lib.adp_mc_run_trace(self.h, C.byref(problem.c), n_traj, seed, traj_id0, n_steps, kind, ta,
+                                              _ptr(fs), _ptr(fsc), _ptr(bs), _ptr(bsc), _ptr(bst), _ptr(oc), int(trace_interval), _ptr(tv), _ptr(tq)))
+        r = dict(final_seq=[bytes(r).decode() for r in fs], final_score=fsc, best_seq=[bytes(r).decode() for r in bs],
+                 best_score=bsc, best_step=bst, outcomes=oc)
+        if tv is not None:
+            r["trace_values"], r["trace_seqs"] = tv, tq      # see adp_mc_run_trace (include/addapt_b200.h) and addapt_b200/trajectory.py
+        return r
 
     def mc_run_raw(self, problem, n_traj, seed, traj_id0, n_steps, thermostat, final_seq=None, final_score=None,
                    best_seq=None, best_score=None, best_step=None, outcomes=None):

@@ -21,6 +21,8 @@ constexpr int kMaxTerms = 16;
 constexpr int kMaxMacro = 8;
 constexpr int kMaxClosure = 16;     // positions changed together by one mutation (a base-pair chain)
 constexpr int kMaxTrain = 512;      // longest training window of the auto-scaling thermostat
+constexpr int kMaxBp = 8;           // base-pair-probability terms (adp_bp_term)
+constexpr int kMaxDensPos = 64;     // positions of all density terms together
 
 struct ScoreProblemDev {
   int32_t n;                         // raw device length
@@ -41,6 +43,19 @@ struct ScoreProblemDev {
   const MotifDev* motif;
   const PfTables* T;
   int32_t n_max;                     // longest contextual length
+  // base-pair-probability terms (adp_bp_term), evaluated from the outside pass of the unconstrained fill of their condition
+  int32_t n_bp;
+  int32_t bp_kind[kMaxBp];           // 0 pair, 1 density
+  int32_t bp_v[kMaxBp];              // variant index of that fill (its `outside` flag is set)
+  int32_t bp_fav[kMaxBp];
+  int32_t bp_at[kMaxBp];             // kind 0: index of the term's query; kind 1: offset of its positions in the density list
+  int32_t bp_npos[kMaxBp];           // kind 1: number of positions
+  double bp_w[kMaxBp];
+  int32_t n_bpq, n_bpd;              // pair queries / density positions in total
+  const int32_t* bp_qi;              // [n_ctx][n_bpq] contextual 0-based positions (device memory)
+  const int32_t* bp_qj;
+  const int32_t* bp_dpos;            // [n_ctx][n_bpd]
+  ADP_HD int n_tot() const { return n_terms + n_bp; }      // term values per context: macrostate terms, then bp terms
 };
 
 // Mutation proposals, precompiled on the host from the macrostate brackets.
@@ -63,6 +78,21 @@ ADP_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, ui
 }
 
 ADP_HD uint8_t complement_nt(uint8_t c) { return c == 'A' ? 'U' : c == 'U' ? 'A' : c == 'G' ? 'C' : c == 'C' ? 'G' : 0; }
+
+// The closure of table slot `slot` written into `seq`: the drawn nucleotide, or its complement, per position
+// (≙ mutate_recursively, reference src/sampling.cc:205-282; the table is compiled on the host, problem_host.h).
+ADP_HD bool closure_changes(const MoveTableDev& mv, int slot, uint8_t nt, const uint8_t* cur) {
+  const uint8_t ntc = complement_nt(nt);
+  bool changed = false;
+  for (int q = 0; q < mv.closure_len[slot]; q++)
+    if (cur[mv.closure_pos[slot][q]] != (mv.closure_comp[slot][q] ? ntc : nt)) changed = true;
+  return changed;
+}
+ADP_HD void apply_closure(const MoveTableDev& mv, int slot, uint8_t nt, uint8_t* seq) {
+  const uint8_t ntc = complement_nt(nt);
+  for (int q = 0; q < mv.closure_len[slot]; q++) seq[mv.closure_pos[slot][q]] = mv.closure_comp[slot][q] ? ntc : nt;
+}
+
 
 // products and sums that must not be contracted into an FMA, so the schedule matches a plain C evaluation
 ADP_HD double mul_rn(double a, double b) {
@@ -97,6 +127,7 @@ struct DesignScratch {
   double* dg;        // [kMaxVariants]
   double* terms;     // [kMaxCtx*kMaxTerms]
   double* bcast;     // [8] broadcast slots
+  double* bp_out;    // [kMaxBp + kMaxDensPos] pair-query / paired-density results of the last fill (device memory; NULL without bp terms)
   double* train;     // [kMaxTrain] score differences the auto-scaling thermostat is trained on: the trajectory's slice of the
                      // device-memory window that is carried from launch to launch (NULL for the other thermostats); touched once a step
 };
@@ -109,6 +140,7 @@ ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
   d.dg = cv.take<double>(kMaxVariants);
   d.terms = cv.take<double>(kMaxCtx * kMaxTerms);
   d.bcast = cv.take<double>(8);
+  d.bp_out = nullptr;     // set by the caller
   d.train = nullptr;      // set by the caller (not in shared memory: 4 KB that the fold working set needs)
 }
 
@@ -120,6 +152,7 @@ template <bool kFast, class E>
 ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint8_t* raw, DesignScratch& d, void* fold_small, double* mats,
                               bool* declined = nullptr, double* dstate = nullptr) {
   double score = 0.;
+  const int nT = sp.n_tot();
   for (int x = 0; x < sp.n_ctx; x++) {
     const int nb = sp.nb[x], na = sp.na[x], nx = nb + sp.n + na;
     for (int p = ex.tid(); p < nx; p += ex.nthreads())
@@ -133,13 +166,26 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
       job.cst = var.cst_id >= 0 ? sp.csts + (size_t)x * sp.n_macro + var.cst_id : nullptr;
       job.motif = var.use_motif ? sp.motif : nullptr;
       job.T = sp.T;
-      job.outside = false;
+      job.outside = var.outside != 0;
       job.dG = d.dg + v;
       job.bppm = nullptr;
       job.n_query = 0;
       job.qi = nullptr; job.qj = nullptr; job.qprobs = nullptr;
+      if (var.outside) {      // base-pair-probability terms read this fill's pair queries and paired densities
+        job.n_query = sp.n_bpq;
+        job.qi = sp.bp_qi + (size_t)x * sp.n_bpq;
+        job.qj = sp.bp_qj + (size_t)x * sp.n_bpq;
+        job.qprobs = d.bp_out;
+        job.n_dens = sp.n_bpd;
+        job.dens_pos = sp.bp_dpos + (size_t)x * sp.n_bpd;
+        job.dens = d.bp_out + kMaxBp;
+      }
       if constexpr (kFast) {
-        if (!run_pf_job_fast(ex, job, fold_small, mats, dstate)) {
+        #if defined(ADP_DESIGN_TWO_INST)
+        if (!run_pf_job_fast<E, false>(ex, job, fold_small, mats, dstate)) {
+#else
+        if (!run_pf_job_fast<E, true>(ex, job, fold_small, mats, dstate)) {
+#endif
           if (declined) *declined = true;
           return 0.;
         }
@@ -147,6 +193,22 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
         run_pf_job(ex, job, fold_small, mats);
       }
       ex.sync();
+      if (var.outside && ex.tid() == 0) {
+        for (int t = 0; t < sp.n_bp; t++) {
+          if (sp.bp_v[t] != v) continue;
+          double p;
+          if (sp.bp_kind[t] == 0) {
+            p = d.bp_out[sp.bp_at[t]];
+          } else {
+            p = 0.;
+            for (int q = 0; q < sp.bp_npos[t]; q++) p += d.bp_out[kMaxBp + sp.bp_at[t] + q];
+            p /= sp.bp_npos[t];
+          }
+          if (!sp.bp_fav[t]) p = 1. - p;
+          d.terms[x * nT + sp.n_terms + t] = log(p);
+        }
+      }
+      if (var.outside) ex.sync();      // the next fill clears bp_out
     }
     if (ex.tid() == 0) {
       for (int t = 0; t < sp.n_terms; t++) {
@@ -154,11 +216,12 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
         if (sp.float_dg) { g0 = (double)(float)g0; g1 = (double)(float)g1; }   // vrna_pf returns float
         double p = exp((g0 - g1) / sp.kT);
         if (!sp.term_fav[t]) p = 1. - p;
-        d.terms[x * sp.n_terms + t] = log(p);
+        d.terms[x * nT + t] = log(p);
       }
     }
     ex.sync();
-    for (int t = 0; t < sp.n_terms; t++) score = add_rn(score, mul_rn(sp.term_w[t], d.terms[x * sp.n_terms + t]));
+    for (int t = 0; t < sp.n_terms; t++) score = add_rn(score, mul_rn(sp.term_w[t], d.terms[x * nT + t]));
+    for (int t = 0; t < sp.n_bp; t++) score = add_rn(score, mul_rn(sp.bp_w[t], d.terms[x * nT + sp.n_terms + t]));
   }
   return score;
 }
@@ -169,8 +232,26 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
 struct McState {
   double cur_score, best_score;
   double T_auto, last_diff;          // auto-scaling thermostat: current temperature, most recent score difference
+  double last_prop, last_crit, last_u;   // trajectory records: proposed score, Metropolis criterion and threshold of the last SCORED step
   int32_t best_step, ntrain;         // best_step = -1: the start sequence; ntrain: filled part of the training window
   uint32_t outcomes[4];              // REJECT, ACCEPT_WORSENED, ACCEPT_UNCHANGED, ACCEPT_IMPROVED
+};
+
+// Optional per-step records of a trajectory, in the columns of the reference's TsvTrajectoryReporter (src/sampling.cc:430-489):
+// every `interval`-th step (step % interval == 0) writes, AFTER the accept / reject decision,
+//   vals[kTraceScalars + nt]: step, current_score, proposed_score, score_diff, temperature, metropolis_criterion,
+//                             random_threshold, outcome, then the nt = n_ctx * n_terms unweighted term values of the LAST evaluated
+//                             proposal (the reference's score_table: it still holds a rejected proposal's terms)
+//   seqs[2 n]:                current sequence, proposed sequence
+// Like in the reference, the proposal columns keep the values of the last scored step across ACCEPT_UNCHANGED steps (which skip
+// the evaluation); before the first scored step the reference leaves score_diff / criterion / threshold uninitialised, here they are 0.
+constexpr int kTraceScalars = 8;
+struct McTrace {
+  int interval;            // 0: no records
+  int cap;                 // records per trajectory: ceil(n_steps / interval)
+  double* vals;            // this trajectory's [cap * (kTraceScalars + nt)]
+  uint8_t* seqs;           // this trajectory's [cap * 2 * n]
+  double* terms_state;     // this trajectory's [nt]: term values carried from launch to launch
 };
 
 // Steps [step0, step1) of one trajectory.  step0 == 0: d.cur holds the start sequence (upper case) and *st is initialised
@@ -180,8 +261,11 @@ struct McState {
 template <bool kFast, class E>
 ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTableDev& mv, uint64_t seed, uint64_t traj_id, int step0, int step1,
                           int thermo_kind, const double* thermo_args, DesignScratch& d, void* fold_small, double* mats, McState* st,
-                          double* dstate = nullptr) {
+                          double* dstate = nullptr, const McTrace* trace = nullptr) {
   const int n = sp.n;
+  const int nt_terms = sp.n_ctx * sp.n_tot();
+  const bool tracing = trace && trace->interval > 0;
+  double last_prop, last_crit, last_u;
   double cur_s, best_s, T_auto, last_diff;
   int best_step, ntrain;
   uint32_t oc0, oc1, oc2, oc3;
@@ -193,12 +277,29 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
     ntrain = 0;
     T_auto = thermo_kind == 2 ? thermo_args[2] : 0.;
     last_diff = 0.;
+    last_prop = last_crit = last_u = 0.;
   } else {
     cur_s = st->cur_score; best_s = st->best_score; best_step = st->best_step;
     oc0 = st->outcomes[0]; oc1 = st->outcomes[1]; oc2 = st->outcomes[2]; oc3 = st->outcomes[3];
     ntrain = st->ntrain; T_auto = st->T_auto; last_diff = st->last_diff;
+    last_prop = st->last_prop; last_crit = st->last_crit; last_u = st->last_u;
+    if (tracing)
+      for (int t = ex.tid(); t < nt_terms; t += ex.nthreads()) d.terms[t] = trace->terms_state[t];
   }
   ex.sync();
+  // one record, after the decision of `step` (collective; see McTrace)
+  auto record = [&](int step, double T, int outcome) {
+    if (!tracing || step % trace->interval != 0) return;
+    const int r = step / trace->interval;
+    if (r >= trace->cap) return;
+    double* v = trace->vals + (size_t)r * (kTraceScalars + nt_terms);
+    uint8_t* q = trace->seqs + (size_t)r * 2 * n;
+    if (ex.tid() == 0) {
+      v[0] = step; v[1] = cur_s; v[2] = last_prop; v[3] = last_diff; v[4] = T; v[5] = last_crit; v[6] = last_u; v[7] = outcome;
+    }
+    for (int t = ex.tid(); t < nt_terms; t += ex.nthreads()) v[kTraceScalars + t] = d.terms[t];
+    for (int p = ex.tid(); p < n; p += ex.nthreads()) { q[p] = d.cur[p]; q[n + p] = d.prop[p]; }
+  };
   // auto-scaling thermostat (kind 2, reference src/sampling.cc:371-401): args = {target acceptance rate, training period,
   // initial temperature}.  Every step appends the most recent score difference (0 before the first scored proposal) to the
   // training set; when it holds `period` values, T = max(median / ln(rate), 0) -- "median" being what nth_element leaves at
@@ -243,25 +344,18 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
       // proposal = current with the closure of the drawn position rewritten
       for (int p = ex.tid(); p < n; p += ex.nthreads()) d.prop[p] = d.cur[p];
       ex.sync();
-      bool changed = false;
-      const int clen = mv.closure_len[slot];
-      const uint8_t ntc = complement_nt(nt);
-      for (int q = 0; q < clen; q++) {
-        const int pos = mv.closure_pos[slot][q];
-        const uint8_t want = mv.closure_comp[slot][q] ? ntc : nt;
-        if (d.cur[pos] != want) changed = true;
-      }
-      if (ex.tid() == 0)
-        for (int q = 0; q < clen; q++) d.prop[mv.closure_pos[slot][q]] = mv.closure_comp[slot][q] ? ntc : nt;
+      const bool changed = closure_changes(mv, slot, nt, d.cur);
+      if (ex.tid() == 0) apply_closure(mv, slot, nt, d.prop);
       ex.sync();
-      if (!changed) { oc2++; continue; }                                       // ACCEPT_UNCHANGED: not scored
+      if (!changed) { oc2++; record(step, T, 2); continue; }                   // ACCEPT_UNCHANGED: not scored
     }
     const double prop_s = score_construct<kFast>(ex, sp, d.prop, d, fold_small, mats, nullptr, dstate);
-    if (start) { cur_s = best_s = prop_s; continue; }
+    if (start) { cur_s = best_s = last_prop = prop_s; continue; }
     const double diff = prop_s - cur_s;
     last_diff = diff;
     const double crit = exp(diff / T);
-    if (crit < u) { oc0++; continue; }                                         // REJECT (NaN compares false: accept)
+    last_prop = prop_s; last_crit = crit; last_u = u;
+    if (crit < u) { oc0++; record(step, T, 0); continue; }                     // REJECT (NaN compares false: accept)
     if (diff > 0) oc3++; else oc1++;
     for (int p = ex.tid(); p < n; p += ex.nthreads()) d.cur[p] = d.prop[p];
     cur_s = prop_s;
@@ -271,13 +365,17 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
       for (int p = ex.tid(); p < n; p += ex.nthreads()) d.best[p] = d.prop[p];
     }
     ex.sync();
+    record(step, T, diff > 0 ? 3 : 1);
   }
   ex.sync();
   if (ex.tid() == 0) {
     st->cur_score = cur_s; st->best_score = best_s; st->best_step = best_step;
     st->outcomes[0] = oc0; st->outcomes[1] = oc1; st->outcomes[2] = oc2; st->outcomes[3] = oc3;
     st->ntrain = ntrain; st->T_auto = T_auto; st->last_diff = last_diff;
+    st->last_prop = last_prop; st->last_crit = last_crit; st->last_u = last_u;
   }
+  if (tracing)
+    for (int t = ex.tid(); t < nt_terms; t += ex.nthreads()) trace->terms_state[t] = d.terms[t];
   ex.sync();
 }
 

@@ -36,7 +36,8 @@ template <bool kFast, int G, bool kSmemMats>
 __global__ void __launch_bounds__(512) score_batch_kernel(const ScoreBatchArgs a) {
   CtaExec<G> ex;
   DesignSmem s = carve_design_smem<kFast, kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
-  const int n = a.sp.n, nt_terms = a.sp.n_ctx * a.sp.n_terms;
+  const int n = a.sp.n, nt_terms = a.sp.n_ctx * a.sp.n_tot();
+  s.d.bp_out = a.bp_out ? a.bp_out + (size_t)blockIdx.x * (kMaxBp + kMaxDensPos) : nullptr;
   if (!kFast && a.only_redo && a.redo[a.B] == 0) return;
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     if (!kFast && a.only_redo && !a.redo[b]) continue;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
   DesignSmem s = carve_design_smem<kFast, kSmemMats>(a.sp.n_max, a.gmats, a.gmat_stride);
   __shared__ McState st;
   const int n = a.sp.n;
+  s.d.bp_out = a.bp_out ? a.bp_out + (size_t)blockIdx.x * (kMaxBp + kMaxDensPos) : nullptr;
   for (int t = blockIdx.x; t < a.n_traj; t += gridDim.x) {
     if (a.step0 == 0) {
       for (int p = threadIdx.x; p < n; p += blockDim.x) s.d.cur[p] = a.init_seq[p];
@@ -73,9 +75,18 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
       if (threadIdx.x == 0) st = a.state[t];
     }
     s.d.train = a.train_state ? a.train_state + (size_t)t * a.train_stride : nullptr;     // the training window stays in device memory
+    McTrace tr;
+    tr.interval = a.trace_interval;
+    tr.cap = a.trace_cap;
+    if (a.trace_interval > 0) {
+      const int nt_terms = a.sp.n_ctx * a.sp.n_tot();
+      tr.vals = a.trace_vals + (size_t)t * a.trace_cap * (kTraceScalars + nt_terms);
+      tr.seqs = a.trace_seqs + (size_t)t * a.trace_cap * 2 * n;
+      tr.terms_state = a.trace_terms_state + (size_t)t * nt_terms;
+    }
     __syncthreads();
     mc_trajectory<kFast>(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.step0, a.step1, a.thermo_kind, a.thermo_args, s.d, s.fold_small,
-                         s.mats, &st, s.dstate);
+                         s.mats, &st, s.dstate, &tr);
     __syncthreads();
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
       a.final_seq[(size_t)t * n + p] = s.d.cur[p];
@@ -93,12 +104,27 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
   }
 }
 
-LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs, bool fast) {
-  LaunchPlan p = fast ? plan_pf_fast(d, n_max, jobs) : plan_pf(d, n_max, jobs, false);
+// One (sequence, slot, nucleotide) triple per thread: the move table's closure applied by the code the Monte-Carlo kernel uses.
+__global__ void mutate_kernel(const MutateArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  uint8_t* out = a.out + (size_t)b * a.n;
+  const uint8_t* in = a.seqs + (size_t)b * a.n;
+  for (int p = 0; p < a.n; p++) out[p] = in[p];
+  if (a.slots[b] >= 0) apply_closure(*a.moves, a.slots[b], a.nts[b], out);
+}
+
+cudaError_t launch_mutate(const MutateArgs& a, cudaStream_t stream) {
+  mutate_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+LaunchPlan plan_design(const DeviceInfo& d, int n_max, int jobs, bool fast, bool outside) {
+  LaunchPlan p = fast ? plan_pf_fast(d, n_max, jobs) : plan_pf(d, n_max, jobs, outside);
   if (fast && !p.threads) return p;
   // same shape as an inside-only fold, plus the design scratch
   const size_t fold_small = fast ? fast_small_bytes(n_max) : pf_small_bytes(n_max);
-  const size_t nmat = fast ? fast_matrix_doubles(n_max) : pf_matrix_doubles(n_max, false);
+  const size_t nmat = fast ? fast_matrix_doubles(n_max) : pf_matrix_doubles(n_max, outside);
   const size_t small = ((fold_small + 15) & ~(size_t)15) + design_extra_bytes(n_max) + 64;
   const size_t mats = nmat * sizeof(double);
   p.mats_in_smem = small + mats <= d.smem_optin;

@@ -15,6 +15,7 @@ struct ScoreBatchArgs {
   size_t gmat_stride;
   int* redo;                 // [B + 1]: designs the fast kernel declined (letters outside ACGU/T); last = their count
   int only_redo;             // general kernel: score only the flagged designs
+  double* bp_out;            // [grid][kMaxBp + kMaxDensPos] scratch of the base-pair-probability terms, or NULL
 };
 
 struct McArgs {
@@ -37,12 +38,30 @@ struct McArgs {
   uint32_t* outcomes;
   double* gmats;
   size_t gmat_stride;
+  // optional per-step records (McTrace): interval 0 = none; buffers are [n_traj][cap][...] / [n_traj][nt]
+  int trace_interval, trace_cap;
+  double* trace_vals;
+  uint8_t* trace_seqs;
+  double* trace_terms_state;
+  double* bp_out;            // [grid][kMaxBp + kMaxDensPos] scratch of the base-pair-probability terms, or NULL
+};
+
+// ≙ mutate_recursively for B (sequence, table slot, nucleotide) triples, see adp_mutate_batch
+struct MutateArgs {
+  const MoveTableDev* moves;
+  int B, n;
+  const uint8_t* seqs;       // B rows of n bytes
+  const int32_t* slots;      // [B] slot of the move table (-1: copy the sequence unchanged)
+  const uint8_t* nts;        // [B] A, C, G or U
+  uint8_t* out;              // B rows of n bytes
 };
 
 // fast = fold with pf_fast.cuh; plan.threads == 0 when n_max is outside its range
-LaunchPlan plan_design(const DeviceInfo&, int n_max, int jobs, bool fast);
+// outside: the fills also run the outside pass (base-pair-probability terms): the general path then needs a third matrix
+LaunchPlan plan_design(const DeviceInfo&, int n_max, int jobs, bool fast, bool outside = false);
 // host_tables: the engine's Boltzmann tables on the host (constant-bank factors of the fast kernels)
 cudaError_t launch_score(const ScoreBatchArgs&, const LaunchPlan&, bool fast, const PfTables* host_tables, cudaStream_t);
 cudaError_t launch_mc(const McArgs&, const LaunchPlan&, bool fast, const PfTables* host_tables, cudaStream_t);
+cudaError_t launch_mutate(const MutateArgs&, cudaStream_t);
 
 }  // namespace adp

@@ -60,7 +60,7 @@ struct adp_engine {
   uint64_t launches = 0;
   // staging / scratch, grown on demand
   DevBuf b_seqs, b_ctxseqs, b_dg, b_bppm, b_qi, b_qj, b_qprobs, b_csts, b_motif, b_gmats, b_e, b_structs;
-  DevBuf b_score, b_terms, b_prob, b_mc[8], b_mcs[4], b_probe, b_redo, b_gmats2;
+  DevBuf b_score, b_terms, b_prob, b_mc[8], b_mcs[8], b_probe, b_redo, b_gmats2, b_bp, b_bpout;
   bool force_general = false;   // tests: route everything through the general kernels
   MotifDev h_motif{};           // last staged motif record (host copy) and its key
   std::string motif_seq, motif_fold;
@@ -240,7 +240,7 @@ void adp_engine_destroy(adp_engine* e) {
   cudaSetDevice(e->device);
   if (e->own_stream) { cudaStreamSynchronize(e->own_stream); }
   DevBuf* bufs[] = {&e->b_seqs, &e->b_ctxseqs, &e->b_dg, &e->b_bppm, &e->b_qi, &e->b_qj, &e->b_qprobs, &e->b_csts, &e->b_motif,
-                    &e->b_gmats, &e->b_e, &e->b_structs, &e->b_score, &e->b_terms, &e->b_prob, &e->b_probe, &e->b_redo, &e->b_gmats2};
+                    &e->b_gmats, &e->b_e, &e->b_structs, &e->b_score, &e->b_terms, &e->b_prob, &e->b_probe, &e->b_redo, &e->b_gmats2, &e->b_bp, &e->b_bpout};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : e->b_mc) b.release();
   for (auto& b : e->b_mcs) b.release();

@@ -23,6 +23,9 @@ struct PfJob {
   const int32_t* qi;
   const int32_t* qj;
   double* qprobs;
+  int n_dens = 0;               // positions (0-based) whose probability of being paired is wanted, answered into dens
+  const int32_t* dens_pos = nullptr;
+  double* dens = nullptr;
 };
 
 ADP_HD size_t pf_small_bytes(int n) { return sizeof(PfSmall) + 16 + ctx_bytes(n) + (size_t)9 * (n + 4) * sizeof(double); }
@@ -80,6 +83,15 @@ ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats)
     if (a > b) { const int t = a; a = b; b = t; }
     job.qprobs[q] = (a != b && a >= 0 && b < n) ? w.pr[tri(a + 1, b + 1)] : 0.;
   }
+  for (int q = ex.tid(); q < job.n_dens; q += ex.nthreads()) {
+    const int p = job.dens_pos[q] + 1;
+    double s = 0.;
+    if (p >= 1 && p <= n) {
+      for (int k = 1; k < p; k++) s += w.pr[tri(k, p)];
+      for (int k = p + 1; k <= n; k++) s += w.pr[tri(p, k)];
+    }
+    job.dens[q] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -87,7 +99,15 @@ ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats)
 // fast_matrix_doubles(n) doubles (shared or global); `dstate`: host emulation only.  Returns false (on every
 // thread, nothing written) when the sequence holds a letter outside ACGU/T -- the caller then uses run_pf_job.
 // `qm_ext` (optional): put Qm there (global scratch, t4_count(n)+2 doubles) instead of behind Qb in `mats`.
-template <class E>
+// kOneCstPath: fold unconstrained jobs through the constrained instantiation too (valid: without a constraint the run lengths
+// span the sequence and every pair is allowed).  The score / Monte-Carlo kernels alternate constrained and unconstrained fills;
+// with one instantiation they keep ONE copy of the sweep (~30 KB of SASS) hot instead of two against a 32 KB instruction cache
+// (ncu, round 2: stall_no_instruction 3.4 -> see profiles/r2_design_icache.md).
+#if defined(ADP_ALWAYS_CST)
+template <class E, bool kOneCstPath = true>
+#else
+template <class E, bool kOneCstPath = false>
+#endif
 ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* mats, double* dstate = nullptr, double* qm_ext = nullptr) {
   const int n = job.n;
 #if defined(ADP_PHASE_PROFILE) && defined(__CUDA_ARCH__)
@@ -128,7 +148,7 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   if (blockIdx.x == 0 && threadIdx.x == 0) printf("prologue %lld cycles\n", clock64() - tp0_);
 #endif
 
-  const double Z = c.has_cst ? fast_inside<true>(ex, c, *H, job.T, mboltz, w) : fast_inside<false>(ex, c, *H, job.T, mboltz, w);
+  const double Z = (kOneCstPath || c.has_cst) ? fast_inside<true>(ex, c, *H, job.T, mboltz, w) : fast_inside<false>(ex, c, *H, job.T, mboltz, w);
   if (ex.tid() == 0)
     *job.dG = Z > 0. ? (-log(Z) - n * log(job.T->pf_scale)) * job.T->kT / 1000. : (double)INFINITY;
   if (!job.outside) return true;
@@ -138,13 +158,17 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   out.qi = job.qi;
   out.qj = job.qj;
   out.qprobs = job.qprobs;
+  out.n_dens = job.n_dens;
+  out.dens_pos = job.dens_pos;
+  out.dens = job.dens;
   if (Z > 0.) {
-    if (c.has_cst) fast_outside<true>(ex, c, *H, job.T, job.motif, mboltz, w, out);
+    if (kOneCstPath || c.has_cst) fast_outside<true>(ex, c, *H, job.T, job.motif, mboltz, w, out);
     else fast_outside<false>(ex, c, *H, job.T, job.motif, mboltz, w, out);
   } else {
     if (job.bppm)
       for (size_t k = ex.tid(); k < (size_t)n * (n + 1) / 2; k += ex.nthreads()) job.bppm[k] = 0.;
     for (int q = ex.tid(); q < job.n_query; q += ex.nthreads()) job.qprobs[q] = 0.;
+    for (int q = ex.tid(); q < job.n_dens; q += ex.nthreads()) job.dens[q] = 0.;
     ex.sync();
   }
   return true;

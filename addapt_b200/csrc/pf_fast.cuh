@@ -72,7 +72,7 @@ constexpr int kFastLevels = 14;       // level sums per thread: s = 4+par, 6+par
 constexpr int kFastMaxN = 320;        // longest construct the fast path takes (ADP_MAX_LEN)
 
 struct PfHot {                        // shared memory, staged once per CTA
-  double FI[256], FM[256];            // mismatch_interior, multiloop stem factor (closing orientation); mismatch_interior_1n = R1 * FI
+  double FI[256];                     // mismatch_interior (closing orientation); mismatch_interior_1n = R1 * FI; multiloop stem factor = RM * FI
   // The matrices hold Qb (inside) / the outside weight PREMULTIPLIED by FI of the pair (inner orientation inside, outer
   // orientation outside), so that the level recursion reads its candidates with one load.  Ratios for the other readers:
   double RI[256], RB[256], R1[256], RM[256];   // 1/FI, terminal-AU factor / FI, F1n / FI, FM / FI  (0 for non-pairs)
@@ -158,12 +158,12 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
     const int x = (a >> 2) + 1, u = (a & 3) + 1, y = (b >> 2) + 1, v = (b & 3) + 1;
     const int t = pair_type(x, y);
     H->FI[q] = t ? T->mmI[t][u][v] : 0.;
-    H->FM[q] = t ? T->mmM[rtype(t)][v][u] * (t > 2 ? T->TermAU : 1.) * T->MLintern : 0.;
+    const double fm = t ? T->mmM[rtype(t)][v][u] * (t > 2 ? T->TermAU : 1.) * T->MLintern : 0.;   // multiloop stem factor
     const double inv = t ? 1. / T->mmI[t][u][v] : 0.;
     H->RI[q] = inv;
     H->RB[q] = t ? (t > 2 ? T->TermAU : 1.) * inv : 0.;
     H->R1[q] = t ? T->mm1nI[t][u][v] * inv : 0.;
-    H->RM[q] = t ? H->FM[q] * inv : 0.;
+    H->RM[q] = t ? fm * inv : 0.;
     H->tyr[q] = (uint8_t)pair_type(v, u);
   }
   for (int q = ex.tid(); q < 32; q += ex.nthreads()) {
@@ -211,7 +211,7 @@ ADP_HD void stage_hot(const E& ex, PfHot* H, const PfTables* T) {
 // The unpaired-prefix half of Qm(i,j), U(i) = sum_u eMLb^u Qm1(i+u,j), obeys U(i) = [i may stay unpaired] eMLb
 // (Qm1(i+1,j) + U(i+1)): one warp evaluates it for the whole column as a scan (two vectors, by column parity), and the
 // dot products of the chunk queue keep only the other half of their terms.
-constexpr int kFastVectors = 18;      // see FastVec (inside pass) / FastVecOut (outside pass)
+constexpr int kFastVectors = 20;      // see FastVec (inside pass) / FastVecOut (outside pass)
 
 struct FastWork {
   double* qb;      // Qb, then (outside) the outside weights: trimmed triangle
@@ -270,7 +270,7 @@ ADP_HD int group_lg(int m, int nt_lg, int cap_lg) {
 // multiloop / exterior stem factor of the pair (i,j) seen from outside (neighbours i-1, j+1 dangle when they exist); same
 // products in the same order as stem_x (fold_common.cuh)
 ADP_HD double fast_stem_ml(const SeqCtx& c, const PfHot& H, const FastWork& w, int type, int i, int j) {
-  if (i > 1 && j < c.n) return H.FM[(w.cn[j] << 4) | w.cp[i]];
+  if (i > 1 && j < c.n) { const int q = (w.cn[j] << 4) | w.cp[i]; return H.RM[q] * H.FI[q]; }
   double e = 1.;
   if (i > 1) e = H.dangle5[type * 5 + c.S[i - 1]];
   else if (j < c.n) e = H.dangle3[type * 5 + c.S[j + 1]];
@@ -364,25 +364,25 @@ struct alignas(16) Int4 { int x, y, z, w; };
 // parity `par` is a run-time (warp-uniform) value, so both parities share one code path: everything that depends on it comes
 // from tables indexed [par][Q] (size factors in the constant bank, row offsets in shared memory) or is folded into the limits
 // (sm1 / sm2 = largest 4 + 2Q that is on for the row / column candidate).  ADDR1 / ADDR2 are the ADDRESSES of the two candidates
-// with u1 = 2 / u2 = 2 and C1 / C2 their hard-constraint gates; a candidate that is off reads the always-zero word `zp` instead, so
-// the step is branch-free: every lane of the warp runs the same instructions whatever its row.  Q is a compile-time constant, so
-// d[] stays in registers.  When unconstrained, the carried sum needs no gate: a level that is off here was off one step earlier
-// on the anti-diagonal too, i.e. it carries zero.
-#define ADP_LEVEL_STEP(Q, ADDR1, C1, ADDR2, C2)                                        \
+// with u1 = 2 / u2 = 2; a candidate that is off reads the always-zero word `zp` instead, so the step is branch-free: every lane of
+// the warp runs the same instructions whatever its row.  Q is a compile-time constant, so d[] stays in registers.
+// Hard constraints cost nothing per level: the gate of a candidate ("the S - 2 bases on the other side may stay unpaired") is
+// monotone in the level, so the caller folds it into sm1 / sm2, and the gate of the carried sum ("i+1 and j-1 may stay unpaired")
+// does not depend on the level, so the caller clears d[] instead.  The carried sum itself needs no limit: a level that is off
+// here was off one step earlier on the anti-diagonal too, i.e. it carries zero.
+#define ADP_LEVEL_STEP(Q, ADDR1, ADDR2)                                                \
   {                                                                                   \
-    const double* p1 = (4 + 2 * (Q) <= sm1 && C1(Q)) ? ADDR1(Q) : zp;                 \
-    const double* p2 = (4 + 2 * (Q) <= sm2 && ((Q) > 0 || par != 0) && C2(Q)) ? ADDR2(Q) : zp; \
+    const double* p1 = (4 + 2 * (Q) <= sm1) ? ADDR1(Q) : zp;                          \
+    const double* p2 = (4 + 2 * (Q) <= sm2 && ((Q) > 0 || par != 0)) ? ADDR2(Q) : zp; \
     double v = fcn[Q] * (*p1 + *p2);                                                  \
-    if ((Q) > 0) v += (!kCst || (4 + 2 * (Q) <= sm && g)) ? d[(Q) > 0 ? (Q) - 1 : 0] : 0.;     \
+    if ((Q) > 0) v += d[(Q) > 0 ? (Q) - 1 : 0];                                       \
     if ((Q) > 0) gen += fci[Q] * v;                                                   \
     d[Q] = v;                                                                         \
   }
-#define ADP_LEVEL_PASS(A1, C1, A2, C2)                                                 \
-  ADP_LEVEL_STEP(13, A1, C1, A2, C2) ADP_LEVEL_STEP(12, A1, C1, A2, C2) ADP_LEVEL_STEP(11, A1, C1, A2, C2) \
-  ADP_LEVEL_STEP(10, A1, C1, A2, C2) ADP_LEVEL_STEP(9, A1, C1, A2, C2) ADP_LEVEL_STEP(8, A1, C1, A2, C2)  \
-  ADP_LEVEL_STEP(7, A1, C1, A2, C2) ADP_LEVEL_STEP(6, A1, C1, A2, C2) ADP_LEVEL_STEP(5, A1, C1, A2, C2)  \
-  ADP_LEVEL_STEP(4, A1, C1, A2, C2) ADP_LEVEL_STEP(3, A1, C1, A2, C2) ADP_LEVEL_STEP(2, A1, C1, A2, C2)  \
-  ADP_LEVEL_STEP(1, A1, C1, A2, C2) ADP_LEVEL_STEP(0, A1, C1, A2, C2)
+#define ADP_LEVEL_PASS(A1, A2)                                                         \
+  ADP_LEVEL_STEP(13, A1, A2) ADP_LEVEL_STEP(12, A1, A2) ADP_LEVEL_STEP(11, A1, A2) ADP_LEVEL_STEP(10, A1, A2) ADP_LEVEL_STEP(9, A1, A2)   \
+  ADP_LEVEL_STEP(8, A1, A2) ADP_LEVEL_STEP(7, A1, A2) ADP_LEVEL_STEP(6, A1, A2) ADP_LEVEL_STEP(5, A1, A2) ADP_LEVEL_STEP(4, A1, A2)     \
+  ADP_LEVEL_STEP(3, A1, A2) ADP_LEVEL_STEP(2, A1, A2) ADP_LEVEL_STEP(1, A1, A2) ADP_LEVEL_STEP(0, A1, A2)
 // the row offsets of one parity: 16 ints, four vector loads
 #define ADP_LEVEL_OFFSETS(LVO)                                                                            \
   int lo[16];                                                                                             \
@@ -530,25 +530,25 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
 #else
         if (sm + par >= 4) {
 #endif
-          const int upr_i1 = kCst ? (int)c.upr[i + 1] : 1000;
-          const bool g = upr_i1 >= 1 && cuj1;
-          const bool ok1 = upr_i1 >= 2, ok2 = upl_j1 >= 2;
-          const int sm1 = sm, sm2 = sm;
-          const int lim1 = upl_j1 - par - 2, lim2 = upr_i1 - par - 2;     // constraint gates: S - 2 unpaired bases on the other side
+          int sm1 = sm, sm2 = sm;
+          if (kCst) {
+            const int upr_i1 = (int)c.upr[i + 1];
+            // constraint gates: two unpaired bases on the candidate's own side, S - 2 on the other side (monotone in the level)
+            const int lim1 = 4 + upl_j1 - par - 2, lim2 = 4 + upr_i1 - par - 2;
+            sm1 = upr_i1 >= 2 ? (sm < lim1 ? sm : lim1) : -1;
+            sm2 = upl_j1 >= 2 ? (sm < lim2 ? sm : lim2) : -1;
+            if (!(upr_i1 >= 1 && cuj1)) { ADP_LEVEL_ZERO() }      // i+1 or j-1 may not stay unpaired: nothing is carried
+          }
           const double* xi = col3 + i + par + 4;       // Qb*FI(i+S-1, jn-3) = xi[2Q]
           const char* qrow = reinterpret_cast<const char*>(qb + i + 2);   // Qb*FI(i+3, l) = qrow[(l-4)(l-5)/2], l = jn+1-S: offset from the table
           const double* fcn = ADP_FC.nin + (par << 4);
           const double* fci = ADP_FC.ip + (par << 4);
           ADP_LEVEL_OFFSETS(lvo + (par << 4))
 #define ADP_A1(Q) reinterpret_cast<const double*>(qrow + lo[Q])
-#define ADP_C1(Q) (!kCst || (ok1 && 2 * (Q) <= lim1))
 #define ADP_A2(Q) (xi + 2 * (Q))
-#define ADP_C2(Q) (!kCst || (ok2 && 2 * (Q) <= lim2))
-          ADP_LEVEL_PASS(ADP_A1, ADP_C1, ADP_A2, ADP_C2)
+          ADP_LEVEL_PASS(ADP_A1, ADP_A2)
 #undef ADP_A1
-#undef ADP_C1
 #undef ADP_A2
-#undef ADP_C2
         } else {
           ADP_LEVEL_ZERO()
         }
@@ -686,8 +686,9 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
   };
 
   ex.sync();
-  // j = 4 is a warm-up turn without cells: it only prepares column 5 (one call site keeps the code small)
-  for (int j = 4; j <= n; j++) {
+  // j = 4 is a warm-up turn without cells: it only prepares column 5; j = n+1 is a run-out turn without cells: it finishes the
+  // exterior prefix of column n and Qm(., n-1), which the outside pass reads (one call site of every piece keeps the code small)
+  for (int j = 4; j <= n + 1; j++) {
     const bool cuj = !kCst || can_unpair(c, j);
     const double* qm1_prev = w.vecp(kVQm1 + (j - 1) % 3);
     double* qm1_cur = w.vecp(kVQm1 + j % 3);
@@ -700,6 +701,11 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       const int l = j + 3 - S;
       w.lvoff[((j & 1) << 5) + t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(double);
     }
+#if !defined(ADP_LEVELS_LAST)
+    // level sums first: every warp runs the same code at the same time (instruction-cache locality), then the warps split
+    // into those that hold cells and those that do the rest of the phase
+    if (j < n) levels(j + 1);
+#endif
     // ---- cells(j): Qb(i,j) for the listed cells, a lane group per cell
     if (m > 0) {
       const double* const hp = w.vecp(kVHp + (j & 1));
@@ -811,7 +817,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
 #endif
           // ---- cell total
           other += cval * ctab;
-          acc = other + au_factor(H, si, sj) * accB + H.R1[codeij] * H.FI[codeij] * acc1n + accML * (H.MLclosing * H.FM[codeij] * H.scale2);
+          acc = other + au_factor(H, si, sj) * accB + H.R1[codeij] * H.FI[codeij] * acc1n + accML * (H.MLclosing * (H.RM[codeij] * H.FI[codeij]) * H.scale2);
         }
         ADP_TICK(11)
         acc = ex.group_sum_rt(acc, Gs);
@@ -829,13 +835,15 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     }
     ADP_TICK(0)
     // ---- everything else of the phase
+#if defined(ADP_LEVELS_LAST)
     if (j < n) levels(j + 1);
+#endif
     ADP_TICK(4)
     if (j < n) list_rows(j + 1);
-    if (j >= 5) rest_rows(j);
+    if (j >= 5 && j <= n) rest_rows(j);
     ADP_TICK(5)
     if (j >= 6 && ex.warp() == nwarp - 1) q1_task(j - 1);
-    if (j >= 6 && ex.warp() == (nwarp > 1 ? nwarp - 2 : 0)) scan_unpaired(j - 1);
+    if (j >= 6 && j <= n && ex.warp() == (nwarp > 1 ? nwarp - 2 : 0)) scan_unpaired(j - 1);
     ADP_TICK(3)
 #if !defined(ADP_X_NOQM)
     if (j >= 7) drain_qm(j - 2);
@@ -844,31 +852,35 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     ex.sync();
     ADP_TICK(7)
   }
-  // epilogue: the exterior prefix of the last column and Qm(., n-1), which the outside pass reads
-  if (n >= 5 && ex.warp() == nwarp - 1) q1_task(n);
-#if !defined(ADP_X_NOQM)
-  if (n >= 6) drain_qm(n - 1);
-#endif
-  ex.sync();
   ADP_PROF_REPORT("inside ")
   return q1[n];
 }
 
 // ---------------------------------------------------------------------------------------------------
 // outside pass.  Overwrites Qb column by column (l = n .. 5) with the outside weights; the probabilities of a
-// column go to `bppm` / the pair queries as soon as the column is complete.
-// vector roles: see FastVecOut.
+// column go to `bppm` / the pair queries one phase after the column is complete.
+//
+// ONE barrier per column, like the inside pass.  Phase l (between barrier l+1 and barrier l) holds
+//   cells(l)        outside weight of every listed pair (k,l), a lane group per cell; the group's first lane also writes the
+//                   pair probability, the exterior-suffix share, the cell's entries of the premultiplied column vectors xA / x1n
+//                   and of the multiloop carrier B of column l-1
+//   rest(l)         rows of column l without a cell: zeros in P / xA / x1n, decay of the carrier B
+//   levels(l-1)     level sums of the generic loops enclosing the cells of the NEXT column (reads columns >= l+2); thread-bound
+//   list(l-1)       the cells of the next column (pairs with a non-zero inside weight)
+//   qln(l-1)        exterior suffix (one thread)
+//   results(l+1)    probabilities of the finished column to bppm / the queries
+//   carriers(l-1)   multiloop carrier A of the next column (reads columns >= l+5), from a queue of warp-sized chunks
+// Double-buffered by column parity: A, B, P, xA, the generic sums, the lists; mod 3: x1n and the counters.
 enum FastVecOut : int {
-  kOA = 2,                                  // A(i,l): multiloop carrier with >= 1 stem right of l
-  kOB = 3,                                  // B(i,l): nothing right of l
-  kOP = 4,                                  // +2: P(.,l) of the finished column, by column parity
-  kOXA = 6,                                 // Pout * terminal factor, column l+1
-  kOX1n = 7,                                // +2: Pout * 1xn mismatch ratio, by column parity
-  kOSx = 9,                                 // exterior stem factor of the cells of the column being prepared
-  kOGen0 = 10, kOGen1 = 11,                 // generic-loop sums per level parity
-  kOQln = 12,                               // exterior suffix Q(l,n)
-  kOAcc = 13,                               // exterior-suffix accumulators
-  kOPm = 14                                 // bound-motif probabilities per site
+  kOA = 2,                                  // +2: A(i,l): multiloop carrier with >= 1 stem right of l, by column parity
+  kOB = 4,                                  // +2: B(i,l): nothing right of l, by column parity
+  kOP = 6,                                  // +2: P(.,l), by column parity
+  kOXA = 8,                                 // +2: Pout * terminal factor, by column parity
+  kOX1n = 10,                               // +3: Pout * 1xn mismatch ratio, by column mod 3
+  kOGen0 = 13, kOGen1 = 15,                 // +2 each: generic-loop sums per level parity, by column parity
+  kOQln = 17,                               // exterior suffix Q(l,n)
+  kOAcc = 18,                               // exterior-suffix accumulators
+  kOPm = 19                                 // bound-motif probabilities per site
 };
 
 struct FastOut {
@@ -877,6 +889,9 @@ struct FastOut {
   const int32_t* qi;
   const int32_t* qj;
   double* qprobs;
+  int n_dens;            // positions (0-based) whose probability of being paired is wanted
+  const int32_t* dens_pos;
+  double* dens;
 };
 
 ADP_HD size_t bppm_index(int n, int i, int j) {      // 1-based i <= j
@@ -888,6 +903,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
                          FastWork& w, const FastOut& out) {
   const int n = c.n, nt = ex.nthreads(), tid = ex.tid(), ld = w.ld, R = w.R;
   const int nt_lg = ilog2_floor((unsigned)nt), warp_lg = ilog2_floor((unsigned)E::kWarp);
+  const int nwarp = nt >> warp_lg;
   const bool mem_state = E::kSerial || w.dstate != nullptr;   // level sums in memory: host emulation, or more anti-diagonals than threads
   const int half = mem_state ? R : (nt >> 1);        // anti-diagonal slots per level parity (>= R)
   double* const qb = w.qb;
@@ -896,14 +912,8 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   const uint8_t* const cp = w.cp;
   for (int k = tid; k < kFastVectors * ld; k += nt)
     if (k >= 2 * ld) w.vbase[k] = 0.;      // everything but q1 and the eMLb powers
-  double* const vA = w.vecp(kOA);
-  double* const vB = w.vecp(kOB);
-  double* const sxv = w.vecp(kOSx);
-  double* const xA = w.vecp(kOXA);
   const double* const q1 = w.vecp(kVQ1);
   const double* const eMLbS = w.vecp(kVEMLb);
-  double* const gen0 = w.vecp(kOGen0);
-  double* const gen1 = w.vecp(kOGen1);
   double* const qln = w.vecp(kOQln);
   double* const accq = w.vecp(kOAcc);
   double* const pm = w.vecp(kOPm);
@@ -912,14 +922,16 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     for (size_t k = tid; k < ntot; k += nt) out.bppm[k] = 0.;
   }
   for (int q = tid; q < out.n_query; q += nt) out.qprobs[q] = 0.;
+  for (int q = tid; q < out.n_dens; q += nt) out.dens[q] = 0.;
   double d[kFastLevels];
   const double* const zp = &H.pad;
   ADP_LEVEL_ZERO()
   ADP_PROF_DECL
   if (mem_state)
     for (int k = tid; k < 2 * R * kFastLevels; k += nt) w.dstate[k] = 0.;
-  if (tid == 0) { w.counter[0] = 0; w.counter[1] = 0; }
-  for (int t = tid; t < 32; t += nt) w.lvoff[t] = 0;
+  if (tid == 0)
+    for (int k = 0; k < 3; k++) { w.counter[k] = 0; w.qctr[k] = 0; }
+  for (int t = tid; t < 64; t += nt) w.lvoff[t] = 0;
   ex.sync();
   if (tid == 0) { qln[n + 1] = 1.; qln[n + 2] = 0.; }
   const double Z = q1[n];
@@ -927,53 +939,57 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   const double s1 = H.scale1, eb1 = H.eMLb1;
   const bool has_motif = motif && motif->len > 0;
 
-  // everything column `ln` needs before its cells can be evaluated; only reads finished columns > ln
-  auto prepare_column = [&](int ln) {
-    const int nr = ln - 4;
-    const int upr_l1 = kCst ? (int)c.upr[ln + 1] : n - ln;           // unpaired run right of ln (0 at the 3' end)
-    // (a) exterior suffix Q(ln,n): position ln unpaired, or paired with some l' >= ln+4 (already accumulated)
-    if (tid == 0) qln[ln] = ((!kCst || can_unpair(c, ln)) ? qln[ln + 1] * s1 : 0.) + accq[ln];
-    // (b) multiloop carriers for every possible 5' closing position i <= ln-5
+  // multiloop carrier A(., ln) for every possible 5' closing position i <= ln-5: rows from a queue, a warp-sized chunk at a time
+  auto carriers = [&](int ln) {
+    const int nrow = ln - 5;
 #if defined(ADP_X_OUT_NOCARRIER)
-    if (false) {
-#else
-    if (ln < n) {
+    if (true) return;
 #endif
-      const int nrow = ln - 5;
-      const bool cul1 = !kCst || can_unpair(c, ln + 1);
-      const int lg = group_lg(nrow > 0 ? nrow : 1, nt_lg, warp_lg);
-      const int Ga = 1 << lg, slotsA = nt >> lg, subA = tid & (Ga - 1);
-      const int gstep = (Ga * (Ga - 1)) >> 1;
-      const int cpl1 = cp[ln + 1];
-      for (int slot0 = 0; slot0 < nrow; slot0 += slotsA) {
-        const int i = slot0 + (tid >> lg) + 1;
-        const bool valid = i <= nrow;
-        double a = 0.;
-        if (valid) {
-          const int cni = cn[i] << 4;
-          int j = ln + 6 + subA;
-          int offp = t4(i, j), offm = t4(ln + 1, j - 1);
-          int stepp = Ga * (j - 4) + gstep;          // column j -> j+Ga (and j-1 -> j-1+Ga is Ga less)
-          const int step2 = Ga * Ga;
-          const uint8_t* pc = cp + j;
-          for (; j <= n; j += Ga) {
-            a += qb[offp] * H.RM[cni | pc[0]] * qm[offm];
-            offp += stepp;
-            offm += stepp - Ga;
-            stepp += step2;
-            pc += Ga;
-          }
-        }
-        a = ex.group_sum_rt(a, Ga) * H.MLclosing;
-        if (valid && subA == 0) {
-          const double c1 = qb[t4(i, ln + 1)] * H.MLclosing * H.RM[(cn[i] << 4) | cpl1];
-          vB[i] = (cul1 ? vB[i] * eb1 : 0.) + c1;
-          vA[i] = a;
+    if (ln >= n || nrow < 1) return;
+    double* const vA = w.vecp(kOA + (ln & 1));
+#if defined(ADP_CARRIER_LG)
+    const int lg = E::kSerial ? 0 : ADP_CARRIER_LG;
+#else
+    const int lg = E::kSerial ? 0 : group_lg(nrow, nt_lg, warp_lg);
+#endif
+    const int Ga = 1 << lg, per = E::kWarp >> lg, subA = ex.lane() & (Ga - 1);
+    const int gstep = (Ga * (Ga - 1)) >> 1;
+    const int nchunk = (nrow + per - 1) / per;
+    int* ctr = w.qctr + (ln % 3);
+    for (;;) {
+      const int ch = grab_chunk(ex, ctr);
+      if (ch >= nchunk) break;
+      const int i = ch * per + (ex.lane() >> lg) + 1;
+      const bool valid = i <= nrow;
+      double a = 0.;
+      if (valid) {
+        const int cni = cn[i] << 4;
+        int j = ln + 6 + subA;
+        int offp = t4(i, j), offm = t4(ln + 1, j - 1);
+        int stepp = Ga * (j - 4) + gstep;          // column j -> j+Ga (and j-1 -> j-1+Ga is Ga less)
+        const int step2 = Ga * Ga;
+        const uint8_t* pc = cp + j;
+        for (; j <= n; j += Ga) {
+          a += qb[offp] * H.RM[cni | pc[0]] * qm[offm];
+          offp += stepp;
+          offm += stepp - Ga;
+          stepp += step2;
+          pc += Ga;
         }
       }
+      a = ex.group_sum_rt(a, Ga) * H.MLclosing;
+      if (valid && subA == 0) vA[i] = a;
     }
-    // (c) level sums of the generic interior loops that enclose (k,ln)
+  };
+
+  // level sums of the generic interior loops that enclose (k,ln) (reads columns >= ln+3)
+  auto levels = [&](int ln) {
+    const int nr = ln - 4;
+    const int upr_l1 = kCst ? (int)c.upr[ln + 1] : n - ln;           // unpaired run right of ln (0 at the 3' end)
     const double* col3 = qb + (((ln - 1) * (ln - 2)) >> 1);           // Pout*FI(i, ln+3) = col3[i - 1]
+    double* const gen0 = w.vecp(kOGen0 + (ln & 1));
+    double* const gen1 = w.vecp(kOGen1 + (ln & 1));
+    const int* const lvo = w.lvoff + ((ln & 1) << 5);
     for (int task = tid; task < 2 * half; task += nt) {
       const int par = task >= half ? 1 : 0;
       int key = task - par * half;
@@ -992,27 +1008,27 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
 #else
         if (k >= 4 && ln + 3 <= n && sm + par >= 4) {
 #endif
-          const int upl_k1 = kCst ? (int)c.upl[k - 1] : 1000;
-          const bool g = upl_k1 >= 1 && upr_l1 >= 1;
-          const bool ok1 = upl_k1 >= 2, ok2 = upr_l1 >= 2;
           const int room1 = n + 1 - ln - par;        // row candidate needs j = ln+S-1 <= n
           const int room2 = k - par;                 // column candidate needs i = k+1-S >= 1
-          const int sm1 = sm < room1 ? sm : room1, sm2 = sm < room2 ? sm : room2;
-          const int lim1 = upr_l1 - par - 2, lim2 = upl_k1 - par - 2;     // constraint gates: S - 2 unpaired bases on the other side
+          int sm1 = sm < room1 ? sm : room1, sm2 = sm < room2 ? sm : room2;
+          if (kCst) {
+            const int upl_k1 = (int)c.upl[k - 1];
+            // constraint gates: two unpaired bases on the candidate's own side, S - 2 on the other side (monotone in the level)
+            const int lim1 = 4 + upr_l1 - par - 2, lim2 = 4 + upl_k1 - par - 2;
+            sm1 = upl_k1 >= 2 ? (sm1 < lim1 ? sm1 : lim1) : -1;
+            sm2 = upr_l1 >= 2 ? (sm2 < lim2 ? sm2 : lim2) : -1;
+            if (!(upl_k1 >= 1 && upr_l1 >= 1)) { ADP_LEVEL_ZERO() }      // k-1 or ln+1 may not stay unpaired: nothing is carried
+          }
           const char* qrow = reinterpret_cast<const char*>(qb + k - 4);   // Pout*FI(k-3, j) = qrow[(j-4)(j-5)/2], j = ln+S-1: offset from the table
           const double* xi = col3 + k - par - 4;     // Pout*FI(k+1-S, ln+3) = xi[-2Q]
           const double* fcn = ADP_FC.nin + (par << 4);
           const double* fci = ADP_FC.ip + (par << 4);
-          ADP_LEVEL_OFFSETS(w.lvoff + (par << 4))
+          ADP_LEVEL_OFFSETS(lvo + (par << 4))
 #define ADP_A1(Q) reinterpret_cast<const double*>(qrow + lo[Q])
-#define ADP_C1(Q) (!kCst || (ok1 && 2 * (Q) <= lim1))
 #define ADP_A2(Q) (xi - 2 * (Q))
-#define ADP_C2(Q) (!kCst || (ok2 && 2 * (Q) <= lim2))
-          ADP_LEVEL_PASS(ADP_A1, ADP_C1, ADP_A2, ADP_C2)
+          ADP_LEVEL_PASS(ADP_A1, ADP_A2)
 #undef ADP_A1
-#undef ADP_C1
 #undef ADP_A2
-#undef ADP_C2
         } else {
           ADP_LEVEL_ZERO()
         }
@@ -1021,43 +1037,109 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       if (mem_state)
         for (int q = 0; q < kFastLevels; q++) w.dstate[(size_t)task * kFastLevels + q] = d[q];
     }
-    ADP_TICK(4)
-    // (d) the cells of this column that carry weight; the column's probability vector starts at zero
-    double* pcol = w.vecp(kOP + (ln & 1));
-    int* counter = w.counter + (ln & 1);
-    ADP_NOUNROLL
-    for (int r = tid; r < nr; r += nt) {
-      const int k = r + 1;
-      pcol[k] = 0.;
-      if (qb[t4(k, ln)] != 0.) {
-        w.cells[ex.atomic_inc(counter)] = (uint16_t)k;
-        sxv[k] = fast_stem_ext(c, H, pair_type(c.S[k], c.S[ln]), k, ln);      // by a thread per row instead of one lane of the cell's group
-      }
-    }
-    ADP_TICK(5)
   };
 
-  ADP_TICK(1)
-  // l = n+1 is a warm-up turn without cells: it only prepares column n (one call site keeps the code small)
-  for (int l = n + 1; l >= kTurn + 2; l--) {
-    const int nr = l <= n ? l - 4 : 0;          // rows k = 1 .. nr
-    double* pcol = w.vecp(kOP + (l & 1));
-    const int m = l <= n ? w.counter[l & 1] : 0;
-    // ---- interval 1: outside weight of every listed pair (k,l); then deferred work
-    {
-      if (tid == 0) w.counter[(l + 1) & 1] = 0;
-      ADP_NOUNROLL
-      for (int t = tid; t < 32; t += nt) {
-        // byte offsets of the row candidates of the level recursion of column l-1: level S reads Pout*FI(k-3, l+S-2)
-        const int S = 4 + (t >> 4) + 2 * (t & 15);
-        const int j = l + S - 2;
-        w.lvoff[t] = (((j - 4) * (j - 5)) >> 1) * (int)sizeof(double);
+  // the cells of column ln that carry weight, rows handed out from the last thread downwards
+  auto list_rows = [&](int ln) {
+    const int nr = ln - 4;
+    uint16_t* const cells = w.cells + (ln & 1) * ld;
+    uint8_t* const iscell = w.iscell + (ln & 1) * ld;
+    int* const counter = w.counter + (ln % 3);
+    const double* const col = qb + t4(1, ln) - 1;
+    ADP_NOUNROLL
+    for (int r = nt - 1 - tid; r < nr; r += nt) {
+      const int k = r + 1;
+      const bool on = col[k] != 0.;
+      iscell[k] = on;
+      if (on) cells[ex.atomic_inc(counter)] = (uint16_t)k;
+    }
+  };
+
+  // rows of column l without a cell (and the three rows behind the column's end, which the filters of later columns may load)
+  auto rest_rows = [&](int l) {
+    const int nr = l - 4;
+    const bool cul = !kCst || can_unpair(c, l);
+    double* const pcol = w.vecp(kOP + (l & 1));
+    double* const xA = w.vecp(kOXA + (l & 1));
+    double* const x1n = w.vecp(kOX1n + l % 3);
+    const double* const vB_old = w.vecp(kOB + (l & 1));
+    double* const vB_new = w.vecp(kOB + ((l - 1) & 1));
+    const uint8_t* const iscell = w.iscell + (l & 1) * ld;
+    ADP_NOUNROLL
+    for (int r = nt - 1 - tid; r < nr + 3; r += nt) {
+      const int k = r + 1;
+      if (k <= nr && iscell[k]) continue;
+      xA[k] = 0.;
+      x1n[k] = 0.;
+      if (k <= nr) {
+        pcol[k] = 0.;
+        if (l < n + 1 && k <= l - 6) vB_new[k] = cul ? vB_old[k] * eb1 : 0.;
       }
+    }
+  };
+
+  // probabilities of the finished column lq: to the full matrix and to the pair queries
+  auto results = [&](int lq) {
+    const int nr = lq - 4;
+    const double* const pcol = w.vecp(kOP + (lq & 1));
+    if (out.bppm)
+      ADP_NOUNROLL
+      for (int r = nt - 1 - tid; r < nr; r += nt)
+        if (pcol[r + 1] != 0.) out.bppm[bppm_index(n, r + 1, lq)] = pcol[r + 1];
+    for (int q = nt - 1 - tid; q < out.n_query; q += nt) {
+      int a = out.qi[q], b = out.qj[q];
+      if (a > b) { const int t = a; a = b; b = t; }
+      if (b + 1 == lq && a >= 0 && a + 1 <= nr) out.qprobs[q] = pcol[a + 1];
+    }
+    // paired probability of the listed positions: position lq collects its whole column, a row position its entry of the
+    // column (one thread per listed position, columns in descending order: a fixed summation order)
+    for (int q = nt - 1 - tid; q < out.n_dens; q += nt) {
+      const int p = out.dens_pos[q] + 1;
+      double s = 0.;
+      if (p == lq) {
+        for (int k = 1; k <= nr; k++) s += pcol[k];
+      } else if (p >= 1 && p <= nr) {
+        s = pcol[p];
+      }
+      if (s != 0.) out.dens[q] += s;
+    }
+  };
+
+  ex.sync();
+  ADP_TICK(1)
+  // l = n+1 is a warm-up turn without cells: it only prepares column n; l = 4 is a run-out turn: it writes the results of
+  // column 5 (one call site of every piece keeps the code small)
+  for (int l = n + 1; l >= kTurn + 1; l--) {
+    const int m = l <= n ? w.counter[l % 3] : 0;
+    if (tid == 0) { w.counter[(l + 1) % 3] = 0; w.qctr[(l + 1) % 3] = 0; }      // the slots of phase l-2 (nobody reads them in this phase)
+    ADP_NOUNROLL
+    for (int t = tid; t < 32; t += nt) {
+      // byte offsets of the row candidates of the level recursion of column l-2 (evaluated in phase l-1): level S reads Pout*FI(k-3, l+S-3)
+      const int S = 4 + (t >> 4) + 2 * (t & 15);
+      const int j = l + S - 3;
+      w.lvoff[((l & 1) << 5) + t] = (((j - 4) * (j - 5)) >> 1) * (int)sizeof(double);
+    }
+#if !defined(ADP_LEVELS_LAST)
+    if (l > kTurn + 2) levels(l - 1);      // first, by every warp at the same time (see the inside pass)
+#endif
+    // ---- cells(l): outside weight of every listed pair (k,l)
+    if (m > 0) {
+      const double* const gen0 = w.vecp(kOGen0 + (l & 1));
+      const double* const gen1 = w.vecp(kOGen1 + (l & 1));
+      const double* const vA = w.vecp(kOA + (l & 1));
+      const double* const vB = w.vecp(kOB + (l & 1));
+      double* const vB_new = w.vecp(kOB + ((l - 1) & 1));
+      double* const pcol = w.vecp(kOP + (l & 1));
+      const double* const xA_rd = w.vecp(kOXA + ((l + 1) & 1));      // column l+1
+      const double* const x1n_rd = w.vecp(kOX1n + (l + 2) % 3);      // column l+2
+      double* const xA_wr = w.vecp(kOXA + (l & 1));
+      double* const x1n_wr = w.vecp(kOX1n + l % 3);
+      const uint16_t* const cells = w.cells + (l & 1) * ld;
       const int lg = group_lg(m, nt_lg, warp_lg);
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
-      const double* x1n_rd = w.vecp(kOX1n + (l & 1));        // column l+2
       const int upr_l1 = kCst ? (int)c.upr[l + 1] : n - l;
-      const int sl = c.S[l], sq1 = c.S[l + 1], cnl = cn[l] << 4;
+      const bool cul = !kCst || can_unpair(c, l);
+      const int sl = c.S[l], cnl = cn[l] << 4, cpl = cp[l];
       int u2cap = upr_l1;                         // also keeps j = l+1+u2 <= n when unconstrained
       if (u2cap > kMaxLoop) u2cap = kMaxLoop;
       if (u2cap > n - l - 1) u2cap = n - l - 1;
@@ -1065,20 +1147,21 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       for (int slot0 = 0; slot0 < m; slot0 += slots) {
         const int slot = slot0 + (tid >> lg);
         const bool valid = slot < m;
-        const int k = valid ? w.cells[slot] : 1;
-        double val = 0.;
-        int type = 0;
+        const int k = valid ? cells[slot] : 1;
+        double val = 0., sx = 0.;      // sx: exterior stem factor of the cell (first lane of the group)
         if (valid) {
           const int sk = c.S[k];
-          type = pair_type(sk, sl);
-          const int sp1 = c.S[k - 1];
+          const int type = pair_type(sk, sl);
           const int codekl = cnl | cp[k];          // inner orientation
           int u1cap = kCst ? (int)c.upl[k - 1] : kMaxLoop;
           if (u1cap > kMaxLoop) u1cap = kMaxLoop;
           if (u1cap > k - 2) u1cap = k - 2;                     // i = k-1-u1 >= 1
           double other = 0., accB = 0., acc1n = 0., accML = 0.;
           double cval = 0., ctab = 0.;
-          if (sub == 0) other = q1[k - 1] * extl * sxv[k] + H.FI[codekl] * (gen0[k] + gen1[k]);
+          if (sub == 0) {
+            sx = fast_stem_ext(c, H, type, k, l);
+            other = q1[k - 1] * extl * sx + H.FI[codekl] * (gen0[k] + gen1[k]);
+          }
           ADP_TICK(8)
           if (k >= 2 && l < n) {
             const int t2r = rtype(type);
@@ -1111,16 +1194,16 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
 #endif
             ADP_TICK(9)
 #if !defined(ADP_X_OUT_NOAXIS)
-            // enclosing bulges with the run on the 3' side: i = k-1, j = l+1+u2, u2 >= 2 -- the four 1-D filters fused into one
-            // loop like in the inside pass: enclosing bulges (i = k-1, j = l+1+u / j = l+1, i = k-1-u: column vector xA), enclosing
-            // 1 x u loops (i = k-2, j = l+1+u, u >= 3) and u x 1 loops (j = l+2, i = k-1-u: column vector x1n).
+            // the four 1-D filters fused into one loop like in the inside pass: enclosing bulges (i = k-1, j = l+1+u / j = l+1,
+            // i = k-1-u: column vector xA), enclosing 1 x u loops (i = k-2, j = l+1+u, u >= 3) and u x 1 loops (j = l+2,
+            // i = k-1-u: column vector x1n).
             {
               int hi13 = u2cap < kMaxLoop - 1 ? u2cap : kMaxLoop - 1, hi31 = u1cap < kMaxLoop - 1 ? u1cap : kMaxLoop - 1;
               if (u1cap < 1) hi13 = -1;
               if (u2cap < 1) hi31 = -1;
               const int hmax = u2cap > u1cap ? u2cap : u1cap;
               const int cni1 = cn[k - 1] << 4, cni2 = k >= 3 ? cn[k - 2] << 4 : 0;
-              const double* xa = xA + k - 1;
+              const double* xa = xA_rd + k - 1;
               const double* xn = x1n_rd + k - 1;
               for (int u = 2 + sub; u <= hmax; u += Gs) {
                 const bool in3 = u <= u2cap;                   // j = l+1+u <= n
@@ -1154,56 +1237,48 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           // ---- cell total
           other += cval * ctab;
           val = other + au_factor(H, sk, sl) * accB + H.R1[codekl] * H.FI[codekl] * acc1n;
-          if (k >= 2 && l < n) val += accML * (H.FM[codekl] * H.scale2);
+          if (k >= 2 && l < n) val += accML * (H.RM[codekl] * H.FI[codekl] * H.scale2);
         }
         ADP_TICK(11)
         val = ex.group_sum_rt(val, Gs);
         ADP_TICK(12)
         if (valid && sub == 0) {
           const int idx = t4(k, l);
+          const int type = pair_type(c.S[k], sl);
           const double qbv = (k > 1 && l < n) ? qb[idx] * H.RI[cnl | cp[k]] : qb[idx];     // back to the plain Qb(k,l)
           pcol[k] = val * qbv;
-          accq[k] += qbv * sxv[k] * qln[l + 1];
+          accq[k] += qbv * sx * qln[l + 1];
           if (has_motif && is_motif_site(c, k, l)) pm[k] = val * fast_hairpin<kCst>(c, H, G, w, motif_boltz, k, l, type);
-          qb[idx] = val * H.FI[(cn[k] << 4) | cp[l]];       // outside weight, premultiplied (outer orientation)
+          const int code = (cn[k] << 4) | cpl;             // outer orientation
+          const double pre = val * H.FI[code];             // outside weight, premultiplied
+          qb[idx] = pre;
+          xA_wr[k] = pre * H.RB[code];
+          x1n_wr[k] = pre * H.R1[code];
+          if (k <= l - 6) vB_new[k] = (cul ? vB[k] * eb1 : 0.) + pre * H.MLclosing * H.RM[code];      // carrier B of column l-1
         }
         ADP_TICK(13)
       }
-      ADP_TICK(0)
     }
-    ex.sync();
-    ADP_TICK(2)
-    // ---- interval 2: premultiplied vectors of the finished column; results; preparation of column l-1
-    {
-      double* x1n_wr = w.vecp(kOX1n + (l & 1));
-      const int cpl = cp[l];
-      ADP_NOUNROLL
-      for (int r = tid; r < nr + 3; r += nt) {
-        const int k = r + 1;
-        double v = 0.;
-        int code = 0;
-        if (k <= nr) { v = qb[t4(k, l)]; code = (cn[k] << 4) | cpl; }     // Pout * FI, outer orientation
-        xA[k] = v * H.RB[code];
-        x1n_wr[k] = v * H.R1[code];
-      }
-      if (out.bppm)
-        ADP_NOUNROLL
-        for (int r = tid; r < nr; r += nt)
-          if (pcol[r + 1] != 0.) out.bppm[bppm_index(n, r + 1, l)] = pcol[r + 1];
-      for (int q = tid; q < out.n_query; q += nt) {
-        int a = out.qi[q], b = out.qj[q];
-        if (a > b) { const int t = a; a = b; b = t; }
-        if (b + 1 == l && a >= 0 && a + 1 <= nr) out.qprobs[q] = pcol[a + 1];
-      }
-      ADP_TICK(3)
-      if (l > kTurn + 2) prepare_column(l - 1);
-      ADP_TICK(6)
-    }
+    ADP_TICK(0)
+    // ---- everything else of the phase
+#if defined(ADP_LEVELS_LAST)
+    if (l > kTurn + 2) levels(l - 1);
+#endif
+    ADP_TICK(4)
+    if (l > kTurn + 2) list_rows(l - 1);
+    if (l <= n && l > kTurn + 1) rest_rows(l);
+    if (l <= n - 1) results(l + 1);
+    // exterior suffix Q(l-1,n): position l-1 unpaired, or paired with some l' >= l+3 (already accumulated)
+    if (l > kTurn + 2 && tid == nt - 1) qln[l - 1] = ((!kCst || can_unpair(c, l - 1)) ? qln[l] * s1 : 0.) + accq[l - 1];
+    ADP_TICK(5)
+    if (l > kTurn + 2) carriers(l - 1);
+    ADP_TICK(6)
     ex.sync();
     ADP_TICK(7)
   }
 
   // the motif's inner pairs inherit the probability of the bound hairpin
+  ex.sync();
   if (has_motif && tid == 0) {
     for (int i = 1; i + motif->len - 1 <= n; i++) {
       if (!c.motif_at[i] || pm[i] == 0.) continue;
@@ -1215,11 +1290,12 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           if (qa > qb_) { const int t = qa; qa = qb_; qb_ = t; }
           if (qa + 1 == a && qb_ + 1 == b) out.qprobs[z] += pm[i];
         }
+        for (int z = 0; z < out.n_dens; z++)
+          if (out.dens_pos[z] + 1 == a || out.dens_pos[z] + 1 == b) out.dens[z] += pm[i];
       }
     }
   }
   ex.sync();
-  ADP_TICK(6)
   ADP_PROF_REPORT("outside")
 }
 

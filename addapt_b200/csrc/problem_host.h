@@ -21,6 +21,8 @@ struct CompiledProblem {
   ScoreProblemDev sp;                    // sp.csts / sp.motif / sp.T are filled in by the caller
   std::vector<ConstraintDev> csts;       // [n_ctx][n_macro]
   bool has_motif = false;
+  std::vector<int32_t> bp_qi, bp_qj, bp_dpos;   // [n_ctx][n_bpq] / [n_ctx][n_bpd]: contextual positions of the bp terms (sp.bp_* point at device copies)
+  bool needs_outside() const { return sp.n_bp > 0; }
 };
 
 // Throws std::string on malformed input.
@@ -30,6 +32,9 @@ inline void compile_problem(const adp_problem& pr, double kT_kcal, CompiledProbl
   if (pr.n < 1 || pr.n > ADP_MAX_LEN) throw std::string("device length out of range");
   if (pr.n_macro < 0 || pr.n_macro > kMaxMacro) throw std::string("too many macrostates (max 8)");
   if (pr.n_terms < 0 || pr.n_terms > kMaxTerms) throw std::string("too many score terms (max 16)");
+  if (pr.n_bp_terms < 0 || pr.n_bp_terms > kMaxBp || pr.n_terms + pr.n_bp_terms > kMaxTerms)
+    throw std::string("too many base-pair-probability terms (max 8, and 16 terms in total)");
+  if (pr.n_bp_terms > 0 && !pr.bp_terms) throw std::string("missing base-pair-probability terms");
   if (pr.n_ctx < 0 || pr.n_ctx > kMaxCtx) throw std::string("too many contexts (max 8)");
   sp.n = pr.n;
   sp.n_ctx = pr.n_ctx > 0 ? pr.n_ctx : 1;
@@ -78,59 +83,119 @@ inline void compile_problem(const adp_problem& pr, double kT_kcal, CompiledProbl
     sp.term_v0[t] = find_or_add(cond, -1);
     sp.term_v1[t] = find_or_add(cond, macro);
   }
+  // base-pair-probability terms: pair queries and density positions of the raw device, shifted per context
+  sp.n_bp = pr.n_bp_terms;
+  std::vector<int> qi, qj, dpos;
+  for (int t = 0; t < sp.n_bp; t++) {
+    const adp_bp_term& b = pr.bp_terms[t];
+    if (b.cond != 0 && b.cond != 1) throw std::string("score term condition must be 0 (apo) or 1 (holo)");
+    sp.bp_kind[t] = b.kind;
+    sp.bp_fav[t] = b.favorable ? 1 : 0;
+    sp.bp_w[t] = b.weight;
+    sp.bp_v[t] = find_or_add(b.cond, -1);
+    sp.variants[sp.bp_v[t]].outside = 1;
+    if (b.kind == 0) {
+      if (b.i < 0 || b.i >= pr.n || b.j < 0 || b.j >= pr.n) throw std::string("pair term position out of range");
+      sp.bp_at[t] = (int)qi.size();
+      sp.bp_npos[t] = 0;
+      qi.push_back(b.i);
+      qj.push_back(b.j);
+    } else if (b.kind == 1) {
+      if (b.n_pos < 1 || !b.pos) throw std::string("density term without positions");
+      sp.bp_at[t] = (int)dpos.size();
+      sp.bp_npos[t] = b.n_pos;
+      for (int q = 0; q < b.n_pos; q++) {
+        if (b.pos[q] < 0 || b.pos[q] >= pr.n) throw std::string("density term position out of range");
+        dpos.push_back(b.pos[q]);
+      }
+      if ((int)dpos.size() > kMaxDensPos) throw std::string("density terms list more than 64 positions");
+    } else {
+      throw std::string("base-pair-probability term kind must be 0 (pair) or 1 (density)");
+    }
+  }
+  sp.n_bpq = (int)qi.size();
+  sp.n_bpd = (int)dpos.size();
+  for (int x = 0; x < sp.n_ctx; x++) {
+    for (size_t q = 0; q < qi.size(); q++) { out->bp_qi.push_back(qi[q] + sp.nb[x]); out->bp_qj.push_back(qj[q] + sp.nb[x]); }
+    for (size_t q = 0; q < dpos.size(); q++) out->bp_dpos.push_back(dpos[q] + sp.nb[x]);
+  }
+  sp.bp_qi = out->bp_qi.data();      // host pointers (the emulation uses them as they are); the engine patches in device copies
+  sp.bp_qj = out->bp_qj.data();
+  sp.bp_dpos = out->bp_dpos.data();
 }
 
-// Throws std::string when a drawn mutation could not be applied (the reference would throw at that step).
-inline void compile_moves(const adp_problem& pr, MoveTableDev* mv) {
-  std::memset(mv, 0, sizeof *mv);
+// Closure of position i under mutate_recursively (reference src/sampling.cc:205-282): every position that has to change with
+// it, alternating nucleotide / complement along every bracket partner in every macrostate.  Throws std::string where the
+// reference would throw (partner not mutable, unbalanced brackets, contradictory pairing, or -- here -- more than kMaxClosure positions).
+inline void compile_closure(const adp_problem& pr, int i, std::vector<int>* order_out, std::vector<int>* parity_out) {
   const int n = pr.n;
   const std::string seq(pr.init_seq, pr.init_seq + n);
   std::vector<std::string> macros;
   for (int m = 0; m < pr.n_macro; m++) macros.emplace_back(pr.macro_cst[m]);
   auto mutable_at = [&](int p) { return std::isupper((unsigned char)seq[p]) != 0; };
-  for (int i = 0; i < n; i++) {
-    if (!mutable_at(i)) continue;
-    bool free_pos = true;
-    for (auto& ms : macros) if (ms[i] == ')') free_pos = false;
-    if (!free_pos) continue;
-    // closure of i: alternate nucleotide / complement along every bracket partner, in every macrostate
-    std::vector<int> parity(n, -1), order;
-    std::vector<std::pair<int, int>> todo{{i, 0}};
-    parity[i] = 0;
-    order.push_back(i);
-    for (size_t head = 0; head < todo.size(); head++) {
-      const int p = todo[head].first, par = todo[head].second;
-      for (auto& ms : macros) {
-        char open, close;
-        int dir;
-        if (ms[p] == '(') { open = '('; close = ')'; dir = 1; }
-        else if (ms[p] == ')') { open = ')'; close = '('; dir = -1; }
-        else continue;
-        int level = 1, q = p;
-        while (level) {
-          q += dir;
-          if (q < 0 || q >= n) throw std::string("mismatched base-pair in a macrostate");
-          if (ms[q] == open) level++;
-          else if (ms[q] == close) level--;
-        }
-        if (!mutable_at(q)) throw std::string("position ") + std::to_string(i) + " cannot be mutated: its partner " + std::to_string(q) + " is not mutable";
-        if (parity[q] < 0) {
-          parity[q] = par ^ 1;
-          order.push_back(q);
-          todo.emplace_back(q, par ^ 1);
-        } else if (parity[q] != (par ^ 1)) {
-          throw std::string("macrostates impose unsatisfiable base-pairing on position ") + std::to_string(i);
-        }
+  if (i < 0 || i >= n) throw std::string("position out of range");
+  if (!mutable_at(i)) throw std::string("position ") + std::to_string(i) + " is not mutable";
+  std::vector<int> parity(n, -1), order;
+  std::vector<std::pair<int, int>> todo{{i, 0}};
+  parity[i] = 0;
+  order.push_back(i);
+  for (size_t head = 0; head < todo.size(); head++) {
+    const int p = todo[head].first, par = todo[head].second;
+    for (auto& ms : macros) {
+      char open, close;
+      int dir;
+      if (ms[p] == '(') { open = '('; close = ')'; dir = 1; }
+      else if (ms[p] == ')') { open = ')'; close = '('; dir = -1; }
+      else continue;
+      int level = 1, q = p;
+      while (level) {
+        q += dir;
+        if (q < 0 || q >= n) throw std::string("mismatched base-pair in a macrostate");
+        if (ms[q] == open) level++;
+        else if (ms[q] == close) level--;
+      }
+      if (!mutable_at(q)) throw std::string("position ") + std::to_string(i) + " cannot be mutated: its partner " + std::to_string(q) + " is not mutable";
+      if (parity[q] < 0) {
+        parity[q] = par ^ 1;
+        order.push_back(q);
+        todo.emplace_back(q, par ^ 1);
+      } else if (parity[q] != (par ^ 1)) {
+        throw std::string("macrostates impose unsatisfiable base-pairing on position ") + std::to_string(i);
       }
     }
-    if ((int)order.size() > kMaxClosure) throw std::string("a mutation would change more than 16 positions");
-    const int slot = mv->n_free++;
-    mv->free_pos[slot] = (int16_t)i;
-    mv->closure_len[slot] = (int8_t)order.size();
-    for (size_t k = 0; k < order.size(); k++) {
-      mv->closure_pos[slot][k] = (int16_t)order[k];
-      mv->closure_comp[slot][k] = (int8_t)parity[order[k]];
-    }
+  }
+  if ((int)order.size() > kMaxClosure) throw std::string("a mutation would change more than 16 positions");
+  *order_out = order;
+  parity_out->assign(order.size(), 0);
+  for (size_t k = 0; k < order.size(); k++) (*parity_out)[k] = parity[order[k]];
+}
+
+inline void store_closure(MoveTableDev* mv, int slot, int i, const std::vector<int>& order, const std::vector<int>& parity) {
+  mv->free_pos[slot] = (int16_t)i;
+  mv->closure_len[slot] = (int8_t)order.size();
+  for (size_t k = 0; k < order.size(); k++) {
+    mv->closure_pos[slot][k] = (int16_t)order[k];
+    mv->closure_comp[slot][k] = (int8_t)parity[k];
+  }
+}
+
+// ≙ can_be_freely_mutated (reference src/sampling.cc:177-193): upper case and not the 3' end of a pair in any macrostate
+inline bool freely_mutable(const adp_problem& pr, int i) {
+  if (i < 0 || i >= pr.n || !std::isupper((unsigned char)pr.init_seq[i])) return false;
+  for (int m = 0; m < pr.n_macro; m++)
+    if (pr.macro_cst[m][i] == ')') return false;
+  return true;
+}
+
+// The proposal table of the Monte-Carlo kernel: one slot per freely mutable position (UnbiasedMutationMove, reference
+// src/sampling.cc:287-303).  Throws std::string when a drawn mutation could not be applied (the reference would throw at that step).
+inline void compile_moves(const adp_problem& pr, MoveTableDev* mv) {
+  std::memset(mv, 0, sizeof *mv);
+  std::vector<int> order, parity;
+  for (int i = 0; i < pr.n; i++) {
+    if (!freely_mutable(pr, i)) continue;
+    compile_closure(pr, i, &order, &parity);
+    store_closure(mv, mv->n_free++, i, order, parity);
   }
 }
 

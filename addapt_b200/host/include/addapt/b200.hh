@@ -54,7 +54,7 @@ class B200RnaFold : public RnaFold {
   mutable vector<double> my_bppm;       // lazily filled by the first base_pair_prob call
 };
 
-// ScoreFunction whose terms are all MacrostateProbTerm: whole batches of candidate sequences of one device are
+// ScoreFunction whose terms are MacrostateProbTerm, PairProbTerm or PairedDensityTerm: whole batches of candidate sequences of one device are
 // scored by one kernel launch.  evaluate(DeviceConstPtr, table&) keeps working (batch of one).
 class B200ScoreFunction : public ScoreFunction {
  public:
@@ -87,11 +87,18 @@ class BatchedMonteCarlo {
  public:
   BatchedMonteCarlo(std::shared_ptr<B200ScoreFunction> scorefxn, int num_steps, ThermostatPtr thermostat);
   vector<BatchedTrajectory> apply(DeviceConstPtr device, int n_traj, uint64_t seed, uint64_t first_id = 0) const;
+  // Also write every trajectory to a file in TsvTrajectoryReporter's layout (reference src/sampling.cc:430-489), one row every
+  // `interval` steps, from the records the kernel keeps (adp_mc_run_trace).  `path` names the file of a single trajectory;
+  // with several, "%d" in it is replaced by the trajectory id, or the id is inserted before the extension (traj.tsv -> traj.17.tsv).
+  void trajectory_files(string path, int interval);
+  static string trajectory_path(string path, uint64_t id, int n_traj);
 
  private:
   std::shared_ptr<B200ScoreFunction> my_scorefxn;
   int my_steps;
   ThermostatPtr my_thermostat;
+  string my_tsv_path;
+  int my_tsv_interval = 0;
 };
 
 }  // namespace addapt

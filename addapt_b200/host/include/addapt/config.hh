@@ -16,6 +16,8 @@ DevicePtr device_from_yaml(vector<string> config_files);
 ScoreFunctionPtr scorefxn_from_yaml(vector<string> config_files);
 // "[not ]<macrostate>"                                                        reference src/config.cc:104-115
 ScoreTermPtr score_term_from_str(ConditionEnum, string spec);
+// "<apo|holo> [not] pair <i> <j> [x <w>]" | "<apo|holo> [not] density <first>-<last> [x <w>]"  (optional `pair_objective` section)
+ScoreTermPtr bp_term_from_str(string spec);
 // optional section `thermostat` (default "1")                                 reference src/config.cc:118-122
 ThermostatPtr thermostat_from_yaml(vector<string> config_files);
 // "<T>" | "<T_hi> to <T_lo> in <N> steps" | "auto [<P>% [<period> [<T0>]]]"   reference src/config.cc:124-175

@@ -104,6 +104,42 @@ class MacrostateProbTerm : public ScoreTerm {
   FavorableEnum my_favorable;
 };
 
+// Score terms over RnaFold::base_pair_prob (reference include/scoring.hh:48).  The mounted snapshot of the reference ships only
+// MacrostateProbTerm, but keeps base_pair_prob on the interface and a fake backend for such terms (tests/test_scoring.cc:12-43);
+// these two restate the historic kinds BASELINE.json's north_star names.  Positions are 0-based indices into the RAW device
+// (a context shifts them by the length of its 5' flank).  B200ScoreFunction evaluates both on the device (adp_bp_term).
+
+// log P(i pairs with j) -- or log(1 - P) -- in one condition ("conditional pairing").  Name: "holo: pair 47-79", "apo: not pair 47-79"
+class PairProbTerm : public ScoreTerm {
+ public:
+  PairProbTerm(int i, int j, ConditionEnum, FavorableEnum = FavorableEnum::YES);
+  double evaluate(DeviceConstPtr, RnaFold const& apo, RnaFold const& holo) const;
+  int i() const { return my_i; }
+  int j() const { return my_j; }
+  ConditionEnum condition() const { return my_condition; }
+  FavorableEnum favorable() const { return my_favorable; }
+
+ private:
+  int my_i, my_j;
+  ConditionEnum my_condition;
+  FavorableEnum my_favorable;
+};
+
+// log of the mean probability of being paired over a set of positions -- or log(1 - mean) -- in one condition ("bppm density")
+class PairedDensityTerm : public ScoreTerm {
+ public:
+  PairedDensityTerm(vector<int> positions, ConditionEnum, FavorableEnum = FavorableEnum::YES);
+  double evaluate(DeviceConstPtr, RnaFold const& apo, RnaFold const& holo) const;
+  vector<int> const& positions() const { return my_positions; }
+  ConditionEnum condition() const { return my_condition; }
+  FavorableEnum favorable() const { return my_favorable; }
+
+ private:
+  vector<int> my_positions;
+  ConditionEnum my_condition;
+  FavorableEnum my_favorable;
+};
+
 }  // namespace addapt
 
 namespace std {

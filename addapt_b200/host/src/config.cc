@@ -130,6 +130,10 @@ ScoreFunctionPtr scorefxn_from_yaml(vector<string> config_files) {
   Section apt = find_section(config_files, "aptamer", REQUIRED);
   scorefxn->aptamer(make_shared<Aptamer>(item_of(apt, "sequence", "aptamer"), item_of(apt, "fold", "aptamer"),
                                          std::stod(item_of(apt, "affinity", "aptamer"))));
+  // optional, beyond the reference's schema: terms over base-pair probabilities, `pair_objective: {name: "<apo|holo> [not] pair <i> <j>
+  // [x <weight>]", name2: "<apo|holo> [not] density <first>-<last> [x <weight>]"}` with 0-based positions of the raw sequence
+  Section bp = find_section(config_files, "pair_objective", OPTIONAL);
+  for (auto const& kv : bp.items) scorefxn->add_term(bp_term_from_str(kv.second));
   Section ctx = find_section(config_files, "contexts", OPTIONAL);
   for (auto const& kv : ctx.items) {
     auto flanks = two_list(kv.second);
@@ -144,6 +148,25 @@ ScoreTermPtr score_term_from_str(ConditionEnum condition, string spec) {
   if (std::regex_match(spec, match, pattern))
     return make_shared<MacrostateProbTerm>(match[2], condition, match[1].matched ? FavorableEnum::NO : FavorableEnum::YES);
   throw msg("can't understand objective: '", spec, "'");
+}
+
+ScoreTermPtr bp_term_from_str(string spec) {
+  static const std::regex pattern("(apo|holo) (not )?(pair|density) ([0-9]+)[ -]([0-9]+)(?: x ([0-9.e+-]+))?");
+  std::smatch m;
+  if (!std::regex_match(spec, m, pattern)) throw msg("can't understand pair objective: '", spec, "'");
+  const ConditionEnum cond = m[1] == "apo" ? ConditionEnum::APO : ConditionEnum::HOLO;
+  const FavorableEnum fav = m[2].matched ? FavorableEnum::NO : FavorableEnum::YES;
+  const int a = std::stoi(m[4]), b = std::stoi(m[5]);
+  ScoreTermPtr term;
+  if (m[3] == "pair") term = make_shared<PairProbTerm>(a, b, cond, fav);
+  else {
+    if (b < a) throw msg("empty position range in '", spec, "'");
+    vector<int> pos;
+    for (int k = a; k <= b; k++) pos.push_back(k);
+    term = make_shared<PairedDensityTerm>(pos, cond, fav);
+  }
+  if (m[6].matched) term->weight(std::stod(m[6]));
+  return term;
 }
 
 ThermostatPtr thermostat_from_yaml(vector<string> config_files) {

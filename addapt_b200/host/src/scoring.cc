@@ -70,6 +70,47 @@ double MacrostateProbTerm::evaluate(DeviceConstPtr device, RnaFold const& apo, R
   return std::log(p);        // may be -inf, exactly like the reference (src/scoring.cc:256-258)
 }
 
+namespace {
+string cond_prefix(ConditionEnum c, FavorableEnum f) { return string(c == ConditionEnum::APO ? "apo" : "holo") + ": " + (f == FavorableEnum::NO ? "not " : ""); }
+int flank5(DeviceConstPtr device) { return device->context() ? (int)device->context()->before().size() : 0; }
+}  // namespace
+
+PairProbTerm::PairProbTerm(int i, int j, ConditionEnum condition, FavorableEnum favorable)
+    : ScoreTerm("pair"), my_i(i), my_j(j), my_condition(condition), my_favorable(favorable) {
+  name(cond_prefix(condition, favorable) + "pair " + std::to_string(i) + "-" + std::to_string(j));
+}
+
+double PairProbTerm::evaluate(DeviceConstPtr device, RnaFold const& apo, RnaFold const& holo) const {
+  if (my_i < 0 || my_j < 0 || my_i >= device->raw_len() || my_j >= device->raw_len()) throw msg("pair term position out of range");
+  RnaFold const& engine = my_condition == ConditionEnum::APO ? apo : holo;
+  const int off = flank5(device);
+  double p = engine.base_pair_prob(my_i + off, my_j + off);
+  if (my_favorable == FavorableEnum::NO) p = 1 - p;
+  return std::log(p);
+}
+
+PairedDensityTerm::PairedDensityTerm(vector<int> positions, ConditionEnum condition, FavorableEnum favorable)
+    : ScoreTerm("density"), my_positions(positions), my_condition(condition), my_favorable(favorable) {
+  string list;
+  for (size_t k = 0; k < positions.size(); k++) list += (k ? "," : "") + std::to_string(positions[k]);
+  name(cond_prefix(condition, favorable) + "paired density " + list);
+}
+
+double PairedDensityTerm::evaluate(DeviceConstPtr device, RnaFold const& apo, RnaFold const& holo) const {
+  if (my_positions.empty()) throw string("density term without positions");
+  RnaFold const& engine = my_condition == ConditionEnum::APO ? apo : holo;
+  const int off = flank5(device), n = device->len();
+  double sum = 0;
+  for (int pos : my_positions) {
+    if (pos < 0 || pos >= device->raw_len()) throw msg("density term position out of range");
+    for (int k = 0; k < n; k++)
+      if (k != pos + off) sum += engine.base_pair_prob(pos + off, k);
+  }
+  double x = sum / (double)my_positions.size();
+  if (my_favorable == FavorableEnum::NO) x = 1 - x;
+  return std::log(x);
+}
+
 }  // namespace addapt
 
 namespace std {

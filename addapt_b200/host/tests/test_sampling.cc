@@ -137,6 +137,17 @@ TEST_CASE(sampling_monte_carlo, "MonteCarlo::apply: greedy at T -> 0, outcome ac
   CHECK(idle.apply(device, rng) == device);
 }
 
+TEST_CASE(config_pair_objective, "bp_term_from_str: the optional pair_objective mini-language") {
+  auto a = std::dynamic_pointer_cast<PairProbTerm>(bp_term_from_str("holo pair 47 79"));
+  CHECK(a && a->i() == 47 && a->j() == 79 && a->condition() == ConditionEnum::HOLO && a->favorable() == FavorableEnum::YES && a->weight() == 1.0);
+  auto b = std::dynamic_pointer_cast<PairProbTerm>(bp_term_from_str("apo not pair 47 79 x 2.5"));
+  CHECK(b && b->favorable() == FavorableEnum::NO && b->condition() == ConditionEnum::APO && b->weight() == 2.5);
+  auto c = std::dynamic_pointer_cast<PairedDensityTerm>(bp_term_from_str("apo density 30-33"));
+  CHECK(c && c->positions() == vector<int>({30, 31, 32, 33}));
+  CHECK_THROWS(bp_term_from_str("holo pairs 1 2"));
+  CHECK_THROWS(bp_term_from_str("apo density 5-4"));
+}
+
 TEST_CASE(config_yaml, "device / score function / thermostat from YAML files (reference src/config.cc:24-122)") {
   const string a = "/tmp/addapt_b200_cfg_a.yml", b = "/tmp/addapt_b200_cfg_b.yml";
   {

@@ -1,6 +1,7 @@
 // The reference's tests/test_scoring.cc: the CPU-side cases use a fake RnaFold (DummyRnaFold, :12-43); the cases
 // that the reference runs against ViennaRNA (:83-259) run here against B200RnaFold on the GPU (--gpu).
 #include <cmath>
+#include <fstream>
 #include <set>
 
 #include "addapt/b200.hh"
@@ -265,4 +266,123 @@ GPU_TEST_CASE(gpu_batched_mc, "BatchedMonteCarlo: sharding-invariant trajectorie
   CHECK(scaled.size() == 2 && scaled[0].best_score >= start - 1e-12);
   class OddThermostat : public Thermostat { double adjust(MonteCarloStep const&) { return 1; } };
   CHECK_THROWS(BatchedMonteCarlo(fx, 10, make_shared<OddThermostat>()).apply(rhf_6, 1, 0));
+}
+
+TEST_CASE(scoring_bp_terms, "PairProbTerm / PairedDensityTerm over a fake base_pair_prob (interface: reference include/scoring.hh:48)") {
+  DevicePtr device = make_shared<Device>("ACGUACGU");
+  auto apo = make_shared<DummyRnaFold>(), holo = make_shared<DummyRnaFold>();
+  (*apo)[{0, 7}] = 0.25;
+  (*holo)[{0, 7}] = 0.9;
+  (*holo)[{1, 6}] = 0.5;
+  (*holo)[{1, 5}] = 0.25;
+  PairProbTerm want(0, 7, ConditionEnum::HOLO), unwanted(7, 0, ConditionEnum::APO, FavorableEnum::NO);
+  CHECK(want.name() == "holo: pair 0-7" && unwanted.name() == "apo: not pair 7-0");
+  CHECK(approx(want.evaluate(device, *apo, *holo), std::log(0.9)));
+  CHECK(approx(unwanted.evaluate(device, *apo, *holo), std::log(0.75)));
+  PairedDensityTerm dens({0, 1, 2}, ConditionEnum::HOLO);
+  CHECK(dens.name() == "holo: paired density 0,1,2");
+  CHECK(approx(dens.evaluate(device, *apo, *holo), std::log((0.9 + 0.75 + 0.0) / 3)));
+  PairedDensityTerm open_({1}, ConditionEnum::HOLO, FavorableEnum::NO);
+  CHECK(approx(open_.evaluate(device, *apo, *holo), std::log(0.25)));
+  // a context shifts the raw positions by its 5' flank
+  DevicePtr flanked = device->copy();
+  flanked->context(make_shared<Context>("GG", "C"));
+  auto shifted = make_shared<DummyRnaFold>();
+  (*shifted)[{2, 9}] = 0.6;
+  CHECK(approx(want.evaluate(flanked, *apo, *shifted), std::log(0.6)));
+  CHECK_THROWS(PairProbTerm(0, 8, ConditionEnum::APO).evaluate(device, *apo, *holo));
+  CHECK_THROWS(PairedDensityTerm({}, ConditionEnum::APO).evaluate(device, *apo, *holo));
+  // through a score function: weights and table rows
+  ScoreFunction fx;
+  fx.fold_factory([&](DeviceConstPtr, AptamerConstPtr apt) -> RnaFoldPtr { return apt ? holo : apo; });
+  fx.aptamer(theo_aptamer());
+  auto t1 = make_shared<PairProbTerm>(0, 7, ConditionEnum::HOLO);
+  t1->weight(2.0);
+  fx.add_term(t1);
+  fx.add_term(make_shared<PairProbTerm>(0, 7, ConditionEnum::APO, FavorableEnum::NO));
+  EvaluatedScoreFunction table;
+  CHECK(approx(fx.evaluate(device, table), 2 * std::log(0.9) + std::log(0.75)));
+  CHECK(table.size() == 2 && table[0].name == "holo: pair 0-7" && table[0].weight == 2.0);
+}
+
+GPU_TEST_CASE(gpu_bp_terms, "bp terms: batched device path == per-object path over B200RnaFold::base_pair_prob") {
+  DevicePtr rhf_6 = rhf_6_device();
+  auto batched = make_shared<B200ScoreFunction>();
+  batched->float_energies(false);
+  batched->aptamer(theo_aptamer());
+  batched->add_term(make_shared<MacrostateProbTerm>("active", ConditionEnum::HOLO, FavorableEnum::YES));
+  batched->add_term(make_shared<PairProbTerm>(47, 79, ConditionEnum::HOLO));
+  batched->add_term(make_shared<PairProbTerm>(47, 79, ConditionEnum::APO, FavorableEnum::NO));
+  batched->add_term(make_shared<PairedDensityTerm>(vector<int>{30, 31, 32, 33, 40, 41, 42, 43}, ConditionEnum::APO));
+  ScoreFunction generic;
+  generic.aptamer(theo_aptamer());
+  for (auto const& t : batched->terms()) generic.add_term(t);
+  EvaluatedScoreFunction ta, tb;
+  const double sa = generic.evaluate(rhf_6, ta), sb = batched->evaluate(rhf_6, tb);
+  CHECK(ta.size() == 4 && tb.size() == 4);
+  for (size_t k = 1; k < 4 && k < ta.size() && k < tb.size(); k++) {      // row 0 goes through float-rounded energies in the generic path
+    CHECK(ta[k].name == tb[k].name);
+    CHECK(approx(ta[k].term, tb[k].term, 1e-6));
+  }
+  CHECK(approx(sa - ta[0].term, sb - tb[0].term, 1e-6));
+  CHECK(tb[1].term > std::log(0.5));                       // the holo-only pair of reference tests/test_scoring.cc:219 forms with the ligand
+  // with contexts the batched path shifts the positions like the per-object path does
+  batched->add_context("rfp", make_shared<Context>("AACTTTCAGTTTAGCGGTCT", ""));
+  generic.add_context("rfp", make_shared<Context>("AACTTTCAGTTTAGCGGTCT", ""));
+  generic.evaluate(rhf_6, ta);
+  batched->evaluate(rhf_6, tb);
+  CHECK(tb.size() == 4 && tb[1].name == "rfp: holo: pair 47-79");
+  for (size_t k = 1; k < 4 && k < ta.size() && k < tb.size(); k++) CHECK(approx(ta[k].term, tb[k].term, 1e-6));
+}
+
+GPU_TEST_CASE(gpu_device_with_own_context, "a device that carries a context is scored with its flanks (reference src/scoring.cc:136-152)") {
+  DevicePtr rhf_6 = rhf_6_device();
+  auto batched = make_shared<B200ScoreFunction>();
+  batched->aptamer(theo_aptamer());
+  batched->add_term(make_shared<MacrostateProbTerm>("active", ConditionEnum::APO, FavorableEnum::NO));
+  batched->add_term(make_shared<MacrostateProbTerm>("active", ConditionEnum::HOLO, FavorableEnum::YES));
+  ScoreFunction generic;
+  generic.aptamer(theo_aptamer());
+  for (auto const& t : batched->terms()) generic.add_term(t);
+  const double bare = batched->evaluate(rhf_6);
+  DevicePtr flanked = rhf_6->copy();
+  flanked->context(make_shared<Context>("GGGGCCACTAGGGACAGGAT", ""));
+  EvaluatedScoreFunction ta, tb;
+  const double sa = generic.evaluate(flanked, ta), sb = batched->evaluate(flanked, tb);
+  CHECK(approx(sa, sb, 1e-4));
+  CHECK(!approx(sb, bare, 1e-6));
+  CHECK(tb.size() == 2 && tb[0].name == "apo: not active" && tb[1].name == "holo: active");
+}
+
+GPU_TEST_CASE(gpu_batched_tsv, "BatchedMonteCarlo writes TsvTrajectoryReporter's file from the kernel's records (reference src/sampling.cc:430-489)") {
+  DevicePtr rhf_6 = rhf_6_device();
+  auto fx = make_shared<B200ScoreFunction>();
+  fx->aptamer(theo_aptamer());
+  fx->add_term(make_shared<MacrostateProbTerm>("active", ConditionEnum::APO, FavorableEnum::NO));
+  fx->add_term(make_shared<MacrostateProbTerm>("active", ConditionEnum::HOLO, FavorableEnum::YES));
+  BatchedMonteCarlo mc(fx, 25, make_shared<AnnealingThermostat>(10, 5.0, 0.0));
+  const string path = "/tmp/addapt_b200_host_test_traj.tsv";
+  mc.trajectory_files(path, 2);
+  auto runs = mc.apply(rhf_6, 2, 42, 0);
+  CHECK(BatchedMonteCarlo::trajectory_path("traj.tsv", 17, 4) == "traj.17.tsv");
+  CHECK(BatchedMonteCarlo::trajectory_path("out/t%d.tsv", 3, 4) == "out/t3.tsv");
+  CHECK(BatchedMonteCarlo::trajectory_path("traj.tsv", 0, 1) == "traj.tsv");
+  for (int t = 0; t < 2; t++) {
+    std::ifstream in(BatchedMonteCarlo::trajectory_path(path, t, 2));
+    CHECK(in.is_open());
+    string line;
+    std::getline(in, line);
+    CHECK(line == "#\tinitial_seq\t" + rhf_6->seq());
+    std::getline(in, line);
+    CHECK(line.rfind("step\tnum_steps\tcurrent_score\tproposed_score\tterm_weight[apo: not active]\tterm_value[apo: not active]\t", 0) == 0);
+    CHECK(line.size() > 30 && line.substr(line.size() - 26) == "current_seq\tproposed_seq\t");
+    int rows = 0;
+    string last;
+    while (std::getline(in, line)) { rows++; last = line; }
+    CHECK(rows == 13);                                     // steps 0, 2, ..., 24
+    CHECK(last.rfind("24\t25\t", 0) == 0);
+    CHECK(last.find("\tUnbiasedMutation\t") != string::npos);
+    // the current sequence of the last record is the final sequence when the record is the last step
+    CHECK(last.find("\t" + runs[t].final_seq + "\t") != string::npos);
+  }
 }

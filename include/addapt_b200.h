@@ -100,6 +100,25 @@ int adp_fold_eval_batch(adp_engine *, int B, int n, const uint8_t *seqs, const a
                         double *dG, double *probs, double *bppm_full);
 
 /* ---- design problem  ≙ Device + ScoreFunction (reference include/model.hh:22-111, include/scoring.hh:97-192) */
+
+/* A score term computed from base-pair probabilities, i.e. from what RnaFold::base_pair_prob returns (reference
+ * include/scoring.hh:48; the fake backend of tests/test_scoring.cc:12-43 exists to test such terms).  The mounted snapshot ships only
+ * MacrostateProbTerm; BASELINE.json's north_star names the two historic kinds, which the engine evaluates on the device from the
+ * outside pass of the UNCONSTRAINED ensemble of the term's condition:
+ *   kind 0, pair:     x = P(i pairs with j)                                  ("conditional pairing": want it in one condition only)
+ *   kind 1, density:  x = mean over the position set of P(position is paired) ("bppm density" of a region)
+ *   term value = log(x) if favorable else log(1 - x); the score adds weight * value, summed over contexts like every term.
+ * Positions are 0-based in the RAW device (contexts shift them). */
+typedef struct {
+  int kind;             /* 0 = pair, 1 = density */
+  int cond;             /* 0 = APO, 1 = HOLO */
+  int favorable;        /* 1 = log(x), 0 = log(1 - x) */
+  double weight;
+  int i, j;             /* kind 0 */
+  int n_pos;            /* kind 1: 1..64 positions (64 in total over all density terms) */
+  const int *pos;
+} adp_bp_term;
+
 typedef struct {
   int n;                          /* raw device length */
   const char *init_seq;           /* mixed case; upper case = mutable (src/sampling.cc:170-175) */
@@ -115,10 +134,13 @@ typedef struct {
   const char *const *ctx_before;
   const char *const *ctx_after;
   int float_dg;                   /* 1: round each ensemble energy through float like vrna_pf's return type */
+  int n_bp_terms;                 /* base-pair-probability terms (0..8; n_terms + n_bp_terms <= 16), evaluated after the macrostate terms */
+  const adp_bp_term *bp_terms;
 } adp_problem;
 
 /* ≙ ScoreFunction::evaluate for B candidate sequences of the same device (reference src/scoring.cc:114-158).
- * seqs: B*n bytes.  score: B doubles.  terms: NULL or B * max(n_ctx,1) * n_terms doubles (unweighted). */
+ * seqs: B*n bytes.  score: B doubles.  terms: NULL or B * max(n_ctx,1) * (n_terms + n_bp_terms) doubles (unweighted;
+ * per context the macrostate terms, then the base-pair-probability terms). */
 int adp_score_batch(adp_engine *, const adp_problem *, int B, const uint8_t *seqs, double *score, double *terms);
 
 /* ≙ MonteCarlo::apply (reference src/sampling.cc:22-107) for n_traj independent trajectories, with
@@ -134,6 +156,31 @@ int adp_mc_run(adp_engine *, const adp_problem *, int n_traj, uint64_t seed, uin
                int thermostat_kind, const double *thermostat_args,
                uint8_t *final_seq, double *final_score, uint8_t *best_seq, double *best_score,
                int32_t *best_step, uint32_t *outcomes);
+
+/* adp_mc_run plus per-step trajectory records in the columns of the reference's TsvTrajectoryReporter (src/sampling.cc:430-489), so
+ * that a GPU run can be written out in the on-disk format the reference's tools read (tools/utils.py:27-51).  Every
+ * trace_interval-th step (step % trace_interval == 0) of every trajectory appends one record, cap = ceil(n_steps / trace_interval)
+ * records per trajectory:
+ *   trace_values: n_traj * cap * adp_mc_trace_width(problem) doubles -- step, current_score, proposed_score, score_diff,
+ *                 temperature, metropolis_criterion, random_threshold, outcome (0 REJECT .. 3 ACCEPT_IMPROVED), then the unweighted
+ *                 term values [context][term] of the last evaluated proposal (the reference's score_table)
+ *   trace_seqs:   n_traj * cap * 2 * n bytes -- current sequence (after the decision), proposed sequence
+ * trace_interval = 0: no records (the buffers may be NULL). */
+int adp_mc_trace_width(const adp_problem *);     /* 8 + max(n_ctx,1) * (n_terms + n_bp_terms) */
+int adp_mc_run_trace(adp_engine *, const adp_problem *, int n_traj, uint64_t seed, uint64_t traj_id0, int n_steps,
+                     int thermostat_kind, const double *thermostat_args,
+                     uint8_t *final_seq, double *final_score, uint8_t *best_seq, double *best_score,
+                     int32_t *best_step, uint32_t *outcomes,
+                     int trace_interval, double *trace_values, uint8_t *trace_seqs);
+
+/* ≙ mutate_recursively(device, position, nucleotide) (reference src/sampling.cc:205-282) and can_be_freely_mutated (:177-193) for B
+ * independent (sequence, position, nucleotide) triples of one design problem: out_seqs[b] = seqs[b] with `position` set to
+ * `nucleotide` and every base-paired partner, in every macrostate, set to the complementary / same nucleotide in turn.  The
+ * closures come from the table compiler and are applied ON THE DEVICE by the code the Monte-Carlo kernel uses for its proposals.
+ * positions (0-based) and nucleotides ('A','C','G','U') are host arrays; freely (may be NULL) receives can_be_freely_mutated.
+ * Fails (ADP_ERR_ARG, text in adp_last_error) where the reference throws: partner not mutable, unbalanced brackets. */
+int adp_mutate_batch(adp_engine *, const adp_problem *, int B, const uint8_t *seqs, const int32_t *positions,
+                     const uint8_t *nucleotides, uint8_t *out_seqs, int32_t *freely_mutable);
 
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 /* Sustained FP64 FMA rate of this GPU (GFMA/s = 1e9 fused multiply-adds per second), measured with a

@@ -23,7 +23,7 @@ static void up(char *dst, const char *src, int n) {
 }
 
 double orc_score(const orc_model *M, const orc_problem *P, const char *seq, int float_dg, double *terms) {
-  int nctx = P->n_ctx > 0 ? P->n_ctx : 1;
+  int nctx = P->n_ctx > 0 ? P->n_ctx : 1, nT = P->n_terms + P->n_bp_terms;
   double kT = orc_kT_kcal(M), score = 0.;
   for (int x = 0; x < nctx; x++) {
     const char *bef = P->n_ctx > 0 ? P->ctx_before[x] : "", *aft = P->n_ctx > 0 ? P->ctx_after[x] : "";
@@ -43,9 +43,42 @@ double orc_score(const orc_model *M, const orc_problem *P, const char *seq, int 
       double p = exp((g0 - g_act) / kT);
       if (!P->term_favorable[t]) p = 1. - p;
       double v = log(p);
-      if (terms) terms[x * P->n_terms + t] = v;
+      if (terms) terms[x * nT + t] = v;
       score += P->term_weight[t] * v;
     }
+    /* terms over base-pair probabilities: full bppm of the unconstrained ensemble of the term's condition, read the way
+     * ViennaRnaFold::base_pair_prob reads it (reference src/scoring.cc:37-51) */
+    double *bp[2] = {NULL, NULL};
+    for (int t = 0; t < P->n_bp_terms; t++) {
+      const orc_bp_term *b = &P->bp_terms[t];
+      int cond = b->cond;
+      if (!bp[cond]) {
+        double g;
+        bp[cond] = (double *)calloc((size_t)n * (n + 1) / 2, sizeof(double));
+        orc_pf(M, n, full, NULL, (cond == 1 && P->motif.seq) ? &P->motif : NULL, &g, bp[cond]);
+      }
+#define ORC_TRI(a_, b_) ((size_t)(a_) * n - (size_t)(a_) * ((a_) - 1) / 2 + ((b_) - (a_)))
+      double xv = 0.;
+      if (b->kind == 0) {
+        int a = b->i + nb, c = b->j + nb;
+        if (a > c) { int q = a; a = c; c = q; }
+        xv = a == c ? 0. : bp[cond][ORC_TRI(a, c)];
+      } else {
+        for (int q = 0; q < b->n_pos; q++) {
+          int p = b->pos[q] + nb;
+          double s = 0.;
+          for (int k = 0; k < p; k++) s += bp[cond][ORC_TRI(k, p)];
+          for (int k = p + 1; k < n; k++) s += bp[cond][ORC_TRI(p, k)];
+          xv += s;
+        }
+        xv /= b->n_pos;
+      }
+      if (!b->favorable) xv = 1. - xv;
+      double v = log(xv);
+      if (terms) terms[x * nT + P->n_terms + t] = v;
+      score += b->weight * v;
+    }
+    free(bp[0]); free(bp[1]);
     free(full); free(cst);
   }
   return score;
@@ -88,9 +121,36 @@ static int mutate_rec(const orc_problem *P, char *seq, int pos, char mut, unsign
   return 0;
 }
 
+int orc_mutate(const orc_problem *P, char *seq, int pos, char nucleotide) {
+  unsigned char *done = (unsigned char *)calloc(P->n, 1);
+  int rc = mutate_rec(P, seq, pos, nucleotide, done);
+  free(done);
+  return rc;
+}
+
+static int mc_run_impl(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t traj, int n_steps, int tk, const double *ta, int float_dg,
+                       char *final_seq, double *final_score, char *best_seq, double *best_score, int32_t *best_step, uint32_t *outcomes, double *trace,
+                       int interval, double *rec_vals, char *rec_seqs);
+
 int orc_mc_run(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t traj, int n_steps, int tk, const double *ta, int float_dg,
                char *final_seq, double *final_score, char *best_seq, double *best_score, int32_t *best_step, uint32_t *outcomes, double *trace) {
+  return mc_run_impl(M, P, seed, traj, n_steps, tk, ta, float_dg, final_seq, final_score, best_seq, best_score, best_step, outcomes, trace, 0, NULL, NULL);
+}
+
+int orc_mc_run_trace(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t traj, int n_steps, int tk, const double *ta, int float_dg,
+                     char *final_seq, double *final_score, char *best_seq, double *best_score, int32_t *best_step, uint32_t *outcomes,
+                     int interval, double *rec_vals, char *rec_seqs) {
+  return mc_run_impl(M, P, seed, traj, n_steps, tk, ta, float_dg, final_seq, final_score, best_seq, best_score, best_step, outcomes, NULL, interval,
+                     rec_vals, rec_seqs);
+}
+
+static int mc_run_impl(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t traj, int n_steps, int tk, const double *ta, int float_dg,
+                       char *final_seq, double *final_score, char *best_seq, double *best_score, int32_t *best_step, uint32_t *outcomes, double *trace,
+                       int interval, double *rec_vals, char *rec_seqs) {
   int n = P->n, nfree = 0;
+  int nterms = (P->n_ctx > 0 ? P->n_ctx : 1) * (P->n_terms + P->n_bp_terms);
+  double *table = (double *)calloc(nterms > 0 ? nterms : 1, sizeof(double));      /* the reference's step.score_table */
+  double last_prop, last_diff_rec = 0., last_crit = 0., last_u = 0.;
   int *freep = (int *)malloc(sizeof(int) * n);
   for (int i = 0; i < n; i++) {
     if (!isupper((unsigned char)P->init_seq[i])) continue;
@@ -101,7 +161,8 @@ int orc_mc_run(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t
   char *cur = (char *)malloc(n + 1), *prop = (char *)malloc(n + 1), *best = (char *)malloc(n + 1);
   unsigned char *done = (unsigned char *)malloc(n);
   memcpy(cur, P->init_seq, n); cur[n] = 0;
-  double cur_s = orc_score(M, P, cur, float_dg, NULL), bs = cur_s;
+  double cur_s = orc_score(M, P, cur, float_dg, table), bs = cur_s;
+  last_prop = cur_s;
   memcpy(best, cur, n + 1);
   int bstep = -1, rc = 0;
   uint32_t oc[4] = {0, 0, 0, 0};
@@ -138,8 +199,9 @@ int orc_mc_run(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t
     int outcome;
     if (!memcmp(prop, cur, n)) outcome = 2;
     else {
-      double ps = orc_score(M, P, prop, float_dg, NULL), d = ps - cur_s, crit = exp(d / T);
+      double ps = orc_score(M, P, prop, float_dg, table), d = ps - cur_s, crit = exp(d / T);
       last_diff = d;
+      last_prop = ps; last_diff_rec = d; last_crit = crit; last_u = u;
       if (crit < u) outcome = 0;
       else {
         outcome = (d > 0) ? 3 : 1;
@@ -149,7 +211,15 @@ int orc_mc_run(const orc_model *M, const orc_problem *P, uint64_t seed, uint64_t
     }
     oc[outcome]++;
     if (trace) trace[i] = cur_s;
+    if (interval > 0 && i % interval == 0) {
+      double *v = rec_vals + (size_t)(i / interval) * (8 + nterms);
+      char *q = rec_seqs + (size_t)(i / interval) * 2 * n;
+      v[0] = i; v[1] = cur_s; v[2] = last_prop; v[3] = last_diff_rec; v[4] = T; v[5] = last_crit; v[6] = last_u; v[7] = outcome;
+      memcpy(v + 8, table, sizeof(double) * nterms);
+      memcpy(q, cur, n); memcpy(q + n, prop, n);
+    }
   }
+  free(table);
   if (final_seq) memcpy(final_seq, cur, n);
   if (final_score) *final_score = cur_s;
   if (best_seq) memcpy(best_seq, best, n);

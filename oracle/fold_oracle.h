@@ -67,6 +67,15 @@ void orc_count_terms(int n, const char *seq, double *w_in, double *w_out);
 /* ------------------------------------------------------------------------------------------
  * Design problem / score / Monte Carlo (reference src/scoring.cc:114-158,233-259 and
  * src/sampling.cc:22-107,170-303,305-338).  Mirrors adp_problem of include/addapt_b200.h. */
+typedef struct {                 /* mirrors adp_bp_term: a term over RnaFold::base_pair_prob (reference include/scoring.hh:48) */
+  int kind;                      /* 0: x = P(i pairs j); 1: x = mean over pos[] of P(position is paired) */
+  int cond, favorable;           /* value = log(x) or log(1-x) in the apo (0) / holo (1) unconstrained ensemble */
+  double weight;
+  int i, j;
+  int n_pos;
+  const int *pos;
+} orc_bp_term;
+
 typedef struct {
   int n;
   const char *init_seq;          /* mixed case; upper = mutable (sampling.cc:170-175) */
@@ -81,9 +90,11 @@ typedef struct {
   int n_ctx;                     /* 0: bare device */
   const char *const *ctx_before;
   const char *const *ctx_after;
+  int n_bp_terms;                /* evaluated after the macrostate terms */
+  const orc_bp_term *bp_terms;
 } orc_problem;
 
-/* score of one upper-case sequence (n chars); terms: n_terms * max(n_ctx,1) values or NULL */
+/* score of one upper-case sequence (n chars); terms: (n_terms + n_bp_terms) * max(n_ctx,1) values or NULL */
 double orc_score(const orc_model *, const orc_problem *, const char *seq, int float_dg, double *terms);
 
 /* Philox4x32-10, key = (seed_lo, seed_hi), counter = (ctr0, ctr1, ctr2, ctr3) */
@@ -96,6 +107,19 @@ int orc_mc_run(const orc_model *, const orc_problem *, uint64_t seed, uint64_t t
                int thermostat_kind, const double *thermostat_args, int float_dg,
                char *final_seq, double *final_score, char *best_seq, double *best_score,
                int32_t *best_step, uint32_t *outcomes, double *score_trace /* n_steps or NULL */);
+
+/* orc_mc_run plus per-step records in the columns of TsvTrajectoryReporter (reference src/sampling.cc:430-489): every
+ * interval-th step writes rec_vals[8 + nterms] = {step, current_score, proposed_score, score_diff, temperature,
+ * metropolis_criterion, random_threshold, outcome, term values of the last evaluated proposal} and rec_seqs[2n] = current,
+ * proposed sequence; proposal columns keep the last scored step's values across ACCEPT_UNCHANGED steps (0 before the first). */
+int orc_mc_run_trace(const orc_model *, const orc_problem *, uint64_t seed, uint64_t traj_id, int n_steps,
+                     int thermostat_kind, const double *thermostat_args, int float_dg,
+                     char *final_seq, double *final_score, char *best_seq, double *best_score,
+                     int32_t *best_step, uint32_t *outcomes, int interval, double *rec_vals, char *rec_seqs);
+
+/* ≙ mutate_recursively(device, pos, nucleotide) (reference src/sampling.cc:205-282) on seq (n chars, mixed case, modified in
+ * place); returns 0, or -1 mismatched brackets, -2 partner not mutable, -3 contradictory pairing */
+int orc_mutate(const orc_problem *, char *seq, int pos, char nucleotide);
 
 #ifdef __cplusplus
 }

@@ -26,11 +26,17 @@ class _Motif(C.Structure):
     _fields_ = [("seq", C.c_char_p), ("fold", C.c_char_p), ("energy_kcal", C.c_double)]
 
 
+class _BpTerm(C.Structure):
+    _fields_ = [("kind", C.c_int), ("cond", C.c_int), ("favorable", C.c_int), ("weight", C.c_double), ("i", C.c_int), ("j", C.c_int),
+                ("n_pos", C.c_int), ("pos", C.POINTER(C.c_int))]
+
+
 class _Problem(C.Structure):
     _fields_ = [("n", C.c_int), ("init_seq", C.c_char_p), ("n_macro", C.c_int), ("macro_cst", C.POINTER(C.c_char_p)),
                 ("n_terms", C.c_int), ("term_macro", C.POINTER(C.c_int)), ("term_cond", C.POINTER(C.c_int)),
                 ("term_favorable", C.POINTER(C.c_int)), ("term_weight", C.POINTER(C.c_double)), ("motif", _Motif),
-                ("n_ctx", C.c_int), ("ctx_before", C.POINTER(C.c_char_p)), ("ctx_after", C.POINTER(C.c_char_p))]
+                ("n_ctx", C.c_int), ("ctx_before", C.POINTER(C.c_char_p)), ("ctx_after", C.POINTER(C.c_char_p)),
+                ("n_bp_terms", C.c_int), ("bp_terms", C.POINTER(_BpTerm))]
 
 
 def _b(s):
@@ -59,6 +65,10 @@ class Oracle:
         L.orc_mc_run.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double),
                                  C.c_int, C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.POINTER(C.c_double),
                                  C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_void_p]
+        L.orc_mc_run_trace.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                       C.c_int, C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.POINTER(C.c_double),
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_mutate.argtypes = [C.POINTER(_Problem), C.c_char_p, C.c_int, C.c_char]
         L.orc_pf_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(_Motif), C.c_void_p, C.c_void_p, C.c_int]
         L.orc_mfe_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(_Motif), C.c_void_p, C.c_void_p, C.c_int]
         L.orc_score_batch.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -144,14 +154,25 @@ class Oracle:
         keep["ca"] = (C.c_char_p * max(len(ctx), 1))(*([_b(c[1]) for c in ctx] or [b""]))
         mo = prob.get("motif")
         m = _Motif(_b(mo[0]), _b(mo[1]), self.kT * math.log(mo[2] / 1e6)) if mo else _Motif(None, None, 0.0)
+        bts = prob.get("bp_terms") or []
+        bp = (_BpTerm * max(len(bts), 1))()
+        keep["bp"], keep["bp_pos"] = bp, []
+        for q, t in enumerate(bts):      # ("pair", cond, favorable, weight, i, j) | ("density", cond, favorable, weight, [positions])
+            bp[q].kind, bp[q].cond, bp[q].favorable, bp[q].weight = (0 if t[0] == "pair" else 1), (1 if t[1] == "holo" else 0), int(bool(t[2])), float(t[3])
+            if t[0] == "pair":
+                bp[q].i, bp[q].j, bp[q].n_pos, bp[q].pos = int(t[4]), int(t[5]), 0, None
+            else:
+                arr = (C.c_int * len(t[4]))(*[int(x) for x in t[4]])
+                keep["bp_pos"].append(arr)
+                bp[q].i, bp[q].j, bp[q].n_pos, bp[q].pos = 0, 0, len(t[4]), arr
         P = _Problem(len(prob["seq"]), _b(prob["seq"]), len(names), keep["macro"], len(T), keep["tm"], keep["tc"], keep["tf"],
-                     keep["tw"], m, len(ctx), keep["cb"], keep["ca"])
+                     keep["tw"], m, len(ctx), keep["cb"], keep["ca"], len(bts), bp)
         keep["P"] = P
         return P, keep
 
     def score(self, prob, seq, float_dg=False, want_terms=False):
         P, keep = self.problem(prob)
-        nt = P.n_terms * max(P.n_ctx, 1)
+        nt = (P.n_terms + P.n_bp_terms) * max(P.n_ctx, 1)
         terms = np.zeros(nt)
         s = self.lib.orc_score(self.model, C.byref(P), _b(seq), int(float_dg), terms.ctypes.data)
         return (s, terms) if want_terms else s
@@ -161,11 +182,20 @@ class Oracle:
         B = len(seqs)
         flat = b"".join(_b(s) for s in seqs)
         out = np.zeros(B)
-        terms = np.zeros((B, P.n_terms * max(P.n_ctx, 1)))
+        terms = np.zeros((B, (P.n_terms + P.n_bp_terms) * max(P.n_ctx, 1)))
         self.lib.orc_score_batch(self.model, C.byref(P), B, flat, int(float_dg), out.ctypes.data, terms.ctypes.data, threads)
         return out, terms
 
-    def mc_run(self, prob, seed, traj_id, n_steps, thermostat=("annealing", 5.0, 0.0, 300), float_dg=False, trace=False):
+    def mutate(self, prob, seq, pos, nucleotide):
+        """≙ mutate_recursively (reference src/sampling.cc:205-282); raises ValueError where the reference throws"""
+        P, keep = self.problem(prob)
+        buf = C.create_string_buffer(_b(seq), len(seq) + 1)
+        rc = self.lib.orc_mutate(C.byref(P), buf, pos, _b(nucleotide))
+        if rc:
+            raise ValueError("mutate_recursively failed rc=%d" % rc)
+        return buf.value.decode()
+
+    def mc_run(self, prob, seed, traj_id, n_steps, thermostat=("annealing", 5.0, 0.0, 300), float_dg=False, trace=False, trace_interval=0):
         P, keep = self.problem(prob)
         n = P.n
         if thermostat[0] == "fixed":
@@ -178,12 +208,19 @@ class Oracle:
         fsc, bsc, bst = C.c_double(), C.c_double(), C.c_int32()
         oc = (C.c_uint32 * 4)()
         tr = np.zeros(n_steps) if trace else None
-        rc = self.lib.orc_mc_run(self.model, C.byref(P), seed, traj_id, n_steps, tk, ta, int(float_dg), fs, C.byref(fsc), bs,
-                                 C.byref(bsc), C.byref(bst), oc, tr.ctypes.data if trace else None)
+        tv = tq = None
+        if trace_interval > 0 and n_steps > 0:
+            cap, width = (n_steps + trace_interval - 1) // trace_interval, 8 + (P.n_terms + P.n_bp_terms) * max(P.n_ctx, 1)
+            tv, tq = np.zeros((cap, width)), np.zeros((cap, 2, n), dtype=np.uint8)
+            rc = self.lib.orc_mc_run_trace(self.model, C.byref(P), seed, traj_id, n_steps, tk, ta, int(float_dg), fs, C.byref(fsc), bs,
+                                           C.byref(bsc), C.byref(bst), oc, trace_interval, tv.ctypes.data, tq.ctypes.data)
+        else:
+            rc = self.lib.orc_mc_run(self.model, C.byref(P), seed, traj_id, n_steps, tk, ta, int(float_dg), fs, C.byref(fsc), bs,
+                                     C.byref(bsc), C.byref(bst), oc, tr.ctypes.data if trace else None)
         if rc:
             raise ValueError("mc_run failed rc=%d" % rc)
         return dict(final_seq=fs.value.decode(), final_score=fsc.value, best_seq=bs.value.decode(), best_score=bsc.value,
-                    best_step=bst.value, outcomes=list(oc), trace=tr)
+                    best_step=bst.value, outcomes=list(oc), trace=tr, trace_values=tv, trace_seqs=tq)
 
     # ---- batches (threaded) --------------------------------------------------------------
     def pf_batch(self, seqs, cst=None, motif=None, bppm=False, threads=0):

@@ -147,13 +147,15 @@ int emu_score(void* model, const adp_problem* pr, int B, const char* seqs, doubl
     cp.sp.T = &M->pf();
     const int nm = cp.sp.n_max;
     std::vector<char> small(std::max(pf_small_bytes(nm), fast_small_bytes(nm)) + 64), extra(design_extra_bytes(nm) + 256);
-    std::vector<double> mats(std::max(pf_matrix_doubles(nm, false), fast_matrix_doubles(nm)) + 2);
+    std::vector<double> mats(std::max(pf_matrix_doubles(nm, cp.needs_outside()), fast_matrix_doubles(nm)) + 2);
     std::vector<double> dstate((size_t)2 * fast_R(nm) * kFastLevels + 2);
     Carver cv(extra.data());
     DesignScratch d;
     carve_design(cv, d, nm);
+    std::vector<double> bp_out(kMaxBp + kMaxDensPos);
+    d.bp_out = bp_out.data();
     SerialExec ex;
-    const int nt = cp.sp.n_ctx * cp.sp.n_terms;
+    const int nt = cp.sp.n_ctx * cp.sp.n_tot();
     for (int b = 0; b < B; b++) {
       std::memcpy(d.cur, seqs + (size_t)b * pr->n, pr->n);
       bool declined = false;
@@ -166,8 +168,34 @@ int emu_score(void* model, const adp_problem* pr, int B, const char* seqs, doubl
   } catch (std::string& er) { g_err = er; return -1; }
 }
 
+int emu_mc_trace(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, int n_steps, int kind, const double* targs,
+                 char* final_seq, double* final_score, char* best_seq, double* best_score, int32_t* best_step, uint32_t* outcomes, int fast,
+                 int interval, double* trace_vals, uint8_t* trace_seqs);
+
 int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, int n_steps, int kind, const double* targs,
            char* final_seq, double* final_score, char* best_seq, double* best_score, int32_t* best_step, uint32_t* outcomes, int fast) {
+  return emu_mc_trace(model, pr, seed, traj_id, n_steps, kind, targs, final_seq, final_score, best_seq, best_score, best_step, outcomes, fast, 0,
+                      nullptr, nullptr);
+}
+
+// ≙ adp_mutate_batch for one triple: the host-compiled closure applied by the device code path (apply_closure)
+int emu_mutate(const adp_problem* pr, const char* seq, int pos, char nt, char* out, int* freely) {
+  try {
+    std::vector<MoveTableDev> mv(1);
+    std::memset(&mv[0], 0, sizeof(MoveTableDev));
+    std::vector<int> order, parity;
+    compile_closure(*pr, pos, &order, &parity);
+    store_closure(&mv[0], 0, pos, order, parity);
+    std::memcpy(out, seq, pr->n);
+    apply_closure(mv[0], 0, (uint8_t)nt, (uint8_t*)out);
+    if (freely) *freely = freely_mutable(*pr, pos) ? 1 : 0;
+    return 0;
+  } catch (std::string& er) { g_err = er; return -1; }
+}
+
+int emu_mc_trace(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, int n_steps, int kind, const double* targs,
+                 char* final_seq, double* final_score, char* best_seq, double* best_score, int32_t* best_step, uint32_t* outcomes, int fast,
+                 int interval, double* trace_vals, uint8_t* trace_seqs) {
   auto* M = (EnergyModel*)model;
   try {
     CompiledProblem cp;
@@ -180,13 +208,21 @@ int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, 
     compile_moves(*pr, &mv[0]);
     const int nm = cp.sp.n_max;
     std::vector<char> small(std::max(pf_small_bytes(nm), fast_small_bytes(nm)) + 64), extra(design_extra_bytes(nm) + 256);
-    std::vector<double> mats(std::max(pf_matrix_doubles(nm, false), fast_matrix_doubles(nm)) + 2);
+    std::vector<double> mats(std::max(pf_matrix_doubles(nm, cp.needs_outside()), fast_matrix_doubles(nm)) + 2);
     std::vector<double> dstate((size_t)2 * fast_R(nm) * kFastLevels + 2);
     Carver cv(extra.data());
     DesignScratch d;
     carve_design(cv, d, nm);
     std::vector<double> train(kMaxTrain);
     d.train = train.data();
+    std::vector<double> bp_out(kMaxBp + kMaxDensPos), terms_state(kMaxCtx * kMaxTerms);
+    d.bp_out = bp_out.data();
+    McTrace tr;
+    tr.interval = interval;
+    tr.cap = interval > 0 ? (n_steps + interval - 1) / interval : 0;
+    tr.vals = trace_vals;
+    tr.seqs = trace_seqs;
+    tr.terms_state = terms_state.data();
     SerialExec ex;
     std::memcpy(d.cur, pr->init_seq, pr->n);
     McState res;
@@ -196,8 +232,8 @@ int emu_mc(void* model, const adp_problem* pr, uint64_t seed, uint64_t traj_id, 
     for (int part = 0; part < 2; part++) {
       const int s0 = part ? cut : 0, s1 = part ? n_steps : cut;
       if (part && cut == 0) break;
-      if (fast) mc_trajectory<true>(ex, cp.sp, mv[0], seed, traj_id, s0, part || cut ? s1 : n_steps, kind, ta, d, small.data(), mats.data(), &res, dstate.data());
-      else mc_trajectory<false>(ex, cp.sp, mv[0], seed, traj_id, s0, part || cut ? s1 : n_steps, kind, ta, d, small.data(), mats.data(), &res);
+      if (fast) mc_trajectory<true>(ex, cp.sp, mv[0], seed, traj_id, s0, part || cut ? s1 : n_steps, kind, ta, d, small.data(), mats.data(), &res, dstate.data(), &tr);
+      else mc_trajectory<false>(ex, cp.sp, mv[0], seed, traj_id, s0, part || cut ? s1 : n_steps, kind, ta, d, small.data(), mats.data(), &res, nullptr, &tr);
     }
     std::memcpy(final_seq, d.cur, pr->n);
     std::memcpy(best_seq, d.best, pr->n);

@@ -100,7 +100,17 @@ class Emu:
             raise self._err()
         return (out, terms) if want_terms else out
 
-    def mc_run(self, problem: Problem, seed, traj_id, n_steps, thermostat=("annealing", 5.0, 0.0, 300), fast=False):
+    def mutate(self, problem: Problem, seq, pos, nucleotide):
+        """one (sequence, position, nucleotide) triple through the table compiler and the device closure code; returns
+        (mutated sequence, can_be_freely_mutated)"""
+        n = problem.n
+        self.lib.emu_mutate.argtypes = [C.POINTER(_Problem), C.c_char_p, C.c_int, C.c_char, C.c_char_p, C.POINTER(C.c_int)]
+        out, free = C.create_string_buffer(n + 1), C.c_int()
+        if self.lib.emu_mutate(C.byref(problem.c), _b(seq), pos, _b(nucleotide), out, C.byref(free)):
+            raise self._err()
+        return out.raw[:n].decode(), bool(free.value)
+
+    def mc_run(self, problem: Problem, seed, traj_id, n_steps, thermostat=("annealing", 5.0, 0.0, 300), fast=False, trace_interval=0):
         n = problem.n
         if thermostat[0] == "fixed":
             kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
@@ -111,8 +121,16 @@ class Emu:
         fs, bs = C.create_string_buffer(n + 1), C.create_string_buffer(n + 1)
         fsc, bsc, bst = C.c_double(), C.c_double(), C.c_int32()
         oc = (C.c_uint32 * 4)()
-        if self.lib.emu_mc(self.model, C.byref(problem.c), seed, traj_id, n_steps, kind, ta, fs, C.byref(fsc), bs, C.byref(bsc),
-                           C.byref(bst), oc, 1 if fast else 0):
+        tv = tq = None
+        if trace_interval > 0 and n_steps > 0:
+            cap = (n_steps + trace_interval - 1) // trace_interval
+            tv, tq = np.zeros((cap, 8 + problem.n_term_values)), np.zeros((cap, 2, n), dtype=np.uint8)
+        self.lib.emu_mc_trace.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                          C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        if self.lib.emu_mc_trace(self.model, C.byref(problem.c), seed, traj_id, n_steps, kind, ta, fs, C.byref(fsc), bs, C.byref(bsc),
+                                 C.byref(bst), oc, 1 if fast else 0, int(trace_interval), tv.ctypes.data if tv is not None else None,
+                                 tq.ctypes.data if tq is not None else None):
             raise self._err()
         return dict(final_seq=fs.raw[:n].decode(), final_score=fsc.value, best_seq=bs.raw[:n].decode(), best_score=bsc.value,
-                    best_step=bst.value, outcomes=list(oc))
+                    best_step=bst.value, outcomes=list(oc), trace_values=tv, trace_seqs=tq)

@@ -1,0 +1,152 @@
+"""CPU side of three rows of the hot-path scope, through the host emulation of the kernel source
+against the oracle and the reference's own known-answer tables:
+  * mutate_recursively / can_be_freely_mutated (reference tests/test_sampling.cc:8-112) through the table compiler and the DEVICE
+    closure code (apply_closure) -- the -m gpu twin is in tests/test_gpu_design.py;
+  * trajectory records in TsvTrajectoryReporter's layout (reference src/sampling.cc:430-489), readable by the reference's loader
+    (tools/utils.py:6-51);
+  * score terms over base-pair probabilities (RnaFold::base_pair_prob, reference include/scoring.hh:48)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from addapt_b200 import trajectory
+from addapt_b200.capi import Problem
+from addapt_b200.sharding import pick_best_scores
+from tests import cases
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REF = json.load(open(os.path.join(GOLD, "reference_thresholds.json")))
+SC_RTOL = 1e-6
+
+
+def table_problem(seq, macros):
+    return Problem(seq, {str(k): m for k, m in enumerate(macros)}, [])
+
+
+def test_mutate_recursively_table_through_the_device_closure_code(emu, oracle):
+    """reference tests/test_sampling.cc:47-99: every row, through compile_closure + apply_closure (what mc_kernel runs)"""
+    for seq, macros, muts, expected in REF["mutate_recursively"]["table"]:
+        pr = table_problem(seq, macros)
+        for i, (nt, want) in enumerate(zip(muts, expected)):
+            got, _ = emu.mutate(pr, seq, i, nt)
+            assert got == want, (seq, macros, i, nt)
+            assert oracle.mutate(pr.as_oracle_dict(), seq, i, nt) == want
+    for seq, macros, i, nt in REF["mutate_recursively"]["throws"]:
+        with pytest.raises(ValueError):
+            emu.mutate(table_problem(seq, macros), seq, i, nt)
+        with pytest.raises(ValueError):
+            oracle.mutate(table_problem(seq, macros).as_oracle_dict(), seq, i, nt)
+
+
+def test_can_be_freely_mutated_table(emu):
+    """reference tests/test_sampling.cc:8-45"""
+    for case in REF["mutable_positions"]["cases"]:
+        pr = table_problem(case["seq"], case["macrostates"])
+        for i, (mut, free) in enumerate(zip(case["can_be_mutated"], case["can_be_freely_mutated"])):
+            if not mut:
+                with pytest.raises(ValueError):          # lower case: mutate_recursively refuses (the reference's Device::mutate throws)
+                    emu.mutate(pr, case["seq"], i, "A")
+                continue
+            try:
+                _, f = emu.mutate(pr, case["seq"], i, "A")
+            except ValueError:
+                assert not free                           # a partner is lower case: the reference would throw at that step
+                continue
+            assert f == bool(free), (case["seq"], i)
+
+
+def _check_trace(a, b, n_terms):
+    """a, b: (values [cap, 8+nt], seqs [cap, 2, n]) of two implementations"""
+    va, qa = a
+    vb, qb = b
+    assert va.shape == vb.shape and np.array_equal(qa, qb)
+    assert np.array_equal(va[:, 0], vb[:, 0]) and np.array_equal(va[:, 7], vb[:, 7])          # step, outcome
+    assert np.array_equal(va[:, 6], vb[:, 6])                                                 # random threshold: bitwise (integer arithmetic)
+    np.testing.assert_allclose(va[:, 4], vb[:, 4], rtol=1e-12)         # temperature: the annealing schedule is bit-equal, the auto-scaling
+                                                                       # one divides by log(rate) of the device's math library
+    for col in (1, 2, 3, 5) + tuple(range(8, 8 + n_terms)):
+        fin = np.isfinite(vb[:, col])
+        assert np.array_equal(np.isfinite(va[:, col]), fin)
+        np.testing.assert_allclose(va[fin, col], vb[fin, col], rtol=1e-5, atol=1e-9)
+
+
+def small_problem(bp=False):
+    seq = "gggaaaCCUGAUACCAGCCGAAAGGCCCUUGGCAGCAGGuuucc"
+    act = "....." + "." * 0 + "(" + "." * 31 + ")" + "......"
+    act = ("." * 6 + "(" + "." * 31 + ")" + "." * 5)[:len(seq)]
+    terms = [("act", "apo", False, 1.0), ("act", "holo", True, 2.0)]
+    bps = [("pair", "holo", True, 0.5, 6, 38), ("density", "apo", False, 1.5, [0, 1, 2, 40, 41]), ("pair", "apo", False, 1.0, 7, 37)] if bp else None
+    return Problem(seq, {"act": act}, terms, motif=cases.THEO, bp_terms=bps)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_trajectory_records_match_the_oracle(emu, oracle, fast):
+    pr = small_problem()
+    for interval, steps in ((1, 24), (5, 23)):
+        e = emu.mc_run(pr, 11, 3, steps, fast=fast, trace_interval=interval)
+        o = oracle.mc_run(pr.as_oracle_dict(), 11, 3, steps, trace_interval=interval)
+        assert e["final_seq"] == o["final_seq"] and e["outcomes"] == o["outcomes"]
+        _check_trace((e["trace_values"], e["trace_seqs"]), (o["trace_values"], o["trace_seqs"]), pr.n_term_values)
+        assert e["trace_values"].shape[0] == (steps + interval - 1) // interval
+        assert list(e["trace_values"][:, 0]) == list(range(0, steps, interval))
+
+
+def test_tsv_is_readable_by_the_reference_loader(emu, tmp_path):
+    """the file has the reference's layout: tools/utils.py:6-31 reads it with pandas.read_table(comment='#') and takes the
+    initial sequence from the first line; tools/utils.py:36-51 picks peaks over the current_score column"""
+    pd = pytest.importorskip("pandas")
+    pr = small_problem()
+    steps = 40
+    r = emu.mc_run(pr, 5, 0, steps, trace_interval=1)
+    path = str(tmp_path / "traj.tsv")
+    trajectory.write_tsv(path, pr, r["trace_values"], r["trace_seqs"], steps)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "#\tinitial_seq\t" + pr.seq
+    assert lines[1].split("\t")[:4] == ["step", "num_steps", "current_score", "proposed_score"]
+    assert lines[1].split("\t")[4:8] == ["term_weight[apo: not act]", "term_value[apo: not act]", "term_weight[holo: act]", "term_value[holo: act]"]
+    assert lines[1].endswith("current_seq\tproposed_seq\t") and lines[2].endswith("\t")
+    with open(path) as f:                                     # load_initial_seq
+        _, label, value = f.readline().split("\t")
+    assert label == "initial_seq" and value.strip() == pr.seq
+    traj = pd.read_table(path, comment="#")                   # load_trajectory
+    assert len(traj) == steps and list(traj["step"]) == list(range(steps)) and set(traj["num_steps"]) == {steps}
+    assert set(traj["outcome"]) <= set(trajectory.OUTCOMES) and set(traj["move"]) == {"UnbiasedMutation"}
+    assert traj["current_seq"].iloc[-1] == r["final_seq"]
+    np.testing.assert_allclose(traj["current_score"].to_numpy(), r["trace_values"][:, 1], rtol=1e-5)
+    counts = [int((traj["outcome"] == name).sum()) for name in trajectory.OUTCOMES]
+    assert counts == r["outcomes"]
+    # peak picking over the column, the reference's way (tools/utils.py:36-51) and the repo's restatement agree
+    scores = traj["current_score"].to_numpy()
+    if scores.min() < np.percentile(scores, 75):
+        ref_scores, peaks = scores.copy(), []
+        blocked, thr = ref_scores.min(), np.percentile(ref_scores, 75)
+        while ref_scores.max() >= thr:
+            i = int(ref_scores.argmax())
+            peaks.append(i)
+            ref_scores[max(i - 3, 0):min(i + 3, len(ref_scores))] = blocked
+        assert pick_best_scores(scores, 3) == sorted(peaks)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_bp_terms_match_the_oracle(emu, oracle, fast):
+    pr = small_problem(bp=True)
+    seqs = [pr.seq.upper(), pr.seq.upper().replace("CCUG", "GCUG", 1), pr.seq.upper().replace("AGG", "UGG", 1)]
+    s1, t1 = emu.score(pr, seqs, want_terms=True, fast=fast)
+    for b, s in enumerate(seqs):
+        s0, t0 = oracle.score(pr.as_oracle_dict(), s, want_terms=True)
+        assert s1[b] == pytest.approx(s0, rel=SC_RTOL)
+        np.testing.assert_allclose(t1[b], t0, rtol=SC_RTOL)
+    assert t1.shape[1] == 5
+    # with contexts the positions shift with the 5' flank
+    prc = Problem(pr.seq, pr.macrostates, pr.terms, motif=cases.THEO, contexts=[("", ""), ("ACGUAC", "GG")], bp_terms=pr.bp_terms)
+    s1, t1 = emu.score(prc, seqs[:1], want_terms=True, fast=fast)
+    s0, t0 = oracle.score(prc.as_oracle_dict(), seqs[0], want_terms=True)
+    assert s1[0] == pytest.approx(s0, rel=SC_RTOL)
+    np.testing.assert_allclose(t1[0], t0, rtol=SC_RTOL)
+    # and a Monte-Carlo run over the extended score function, step for step
+    e = emu.mc_run(pr, 3, 1, 12, fast=fast, trace_interval=1)
+    o = oracle.mc_run(pr.as_oracle_dict(), 3, 1, 12, trace_interval=1)
+    assert e["final_seq"] == o["final_seq"] and e["outcomes"] == o["outcomes"]
+    _check_trace((e["trace_values"], e["trace_seqs"]), (o["trace_values"], o["trace_seqs"]), pr.n_term_values)

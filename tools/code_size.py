@@ -34,14 +34,16 @@ if KERNEL == "pf":
     ins_a, out_a = find("ADP_HD double fast_inside("), find("ADP_HD void fast_outside(")
 else:
     ins_a, out_a = find("ADP_HD int mfe_fast_fill("), len(src) + 1
-MI = [("ADP_HD double fast_inside(", "in.init"), ("auto prepare_column", "in.levels"), ("double* ext_n", "in.rows"), ("auto drain_qm", "in.qm"),
-      ("// j = 4 is a warm-up", "in.colhead"), ("// ---- interval 1: Qb(i,j)", "in.cells.head"), ("// corner candidates through", "in.cells.corners"),
-      ("// bulges with the unpaired run on the 3' side", "in.cells.axis"), ("// multiloop closed by (i,j)", "in.cells.ml"), ("// ---- cell total", "in.cells.fin"),
-      ("// ---- interval 2: premultiplied", "in.int2")]
-MO = [("ADP_HD void fast_outside(", "out.init"), ("auto prepare_column", "out.carriers"), ("// (c) level sums", "out.levels"), ("// (d) the cells of this column", "out.rows"),
-      ("// l = n+1 is a warm-up", "out.colhead"), ("// ---- interval 1: outside weight", "out.cells.head"), ("const int t2r = rtype(type);", "out.cells.corners"),
-      ("// enclosing bulges with the run on the 3' side", "out.cells.axis"), ("// (k,l) is a stem of a multiloop", "out.cells.ml"), ("// ---- cell total", "out.cells.fin"),
-      ("// ---- interval 2: premultiplied", "out.int2"), ("// the motif's inner pairs", "out.motif")]
+MI = [("ADP_HD double fast_inside(", "in.init"), ("auto levels = [&](int jn)", "in.levels"), ("auto list_rows = [&](int jn)", "in.list"), ("auto rest_rows = [&](int j)", "in.rest"),
+      ("auto q1_task", "in.q1"), ("auto scan_unpaired", "in.scan"), ("auto drain_qm", "in.qm"),
+      ("// j = 4 is a warm-up", "in.colhead"), ("// ---- cells(j): Qb(i,j)", "in.cells.head"), ("// corner candidates through", "in.cells.corners"),
+      ("// The four 1-D filters along", "in.cells.axis"), ("// multiloop closed by (i,j)", "in.cells.ml"), ("// ---- cell total", "in.cells.fin"),
+      ("// ---- everything else of the phase", "in.tail"), ("// epilogue: the exterior prefix", "in.epilogue")]
+MO = [("ADP_HD void fast_outside(", "out.init"), ("auto carriers = [&](int ln)", "out.carriers"), ("auto levels = [&](int ln)", "out.levels"), ("auto list_rows = [&](int ln)", "out.list"),
+      ("auto rest_rows = [&](int l)", "out.rest"), ("auto results = [&](int lq)", "out.results"),
+      ("// l = n+1 is a warm-up", "out.colhead"), ("// ---- cells(l): outside weight", "out.cells.head"), ("const int t2r = rtype(type);", "out.cells.corners"),
+      ("// the four 1-D filters fused into one loop like", "out.cells.axis"), ("// (k,l) is a stem of a multiloop", "out.cells.ml"), ("// ---- cell total", "out.cells.fin"),
+      ("// ---- everything else of the phase", "out.tail"), ("// the motif's inner pairs", "out.motif")]
 MM = [("ADP_HD int mfe_fast_fill(", "fill.init"), ("auto prepare_column", "fill.levels"), ("      const int prev = fm1_prev[r + 1];", "fill.rows"),
       ("// j = 4 is a warm-up", "fill.colhead"), ("// ---- interval 1: C(i,j)", "fill.cells.head"), ("// corner candidates, software-pipelined", "fill.cells.corners"),
       ("// the four 1-D filters along", "fill.cells.axis"), ("int k = i + 6 + sub;", "fill.cells.ml"), ("other = imin(other, cadd + ctab);", "fill.cells.fin"),
