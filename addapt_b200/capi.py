@@ -135,6 +135,7 @@ def load_library():
         L.adp_mc_trace_width.argtypes = [C.POINTER(_Problem)]
         L.adp_mc_run_trace.argtypes = [vp, C.POINTER(_Problem), ci, C.c_uint64, C.c_uint64, ci, ci, C.POINTER(cd), vp, vp, vp, vp, vp, vp, ci, vp, vp]
         L.adp_mutate_batch.argtypes = [vp, C.POINTER(_Problem), ci, vp, vp, vp, vp, vp]
+        L.adp_top_k.argtypes = [vp, ci, vp, ci, vp, vp]
     _LIB = L
     return L
 
@@ -296,6 +297,17 @@ class Engine:
 
     def score_raw(self, problem, B, seqs, score, terms=None):
         self._check(self.lib.adp_score_batch(self.h, C.byref(problem.c), B, _ptr(seqs), _ptr(score), _ptr(terms)))
+
+    def top_k(self, scores, k):
+        """indices and values of the k best scores (largest first, ties by lower index, NaN last), selected on the device"""
+        s = np.ascontiguousarray(scores, dtype=np.float64)
+        k = min(int(k), s.shape[0])
+        idx, top = np.zeros(k, dtype=np.int32), np.zeros(k)
+        self._check(self.lib.adp_top_k(self.h, s.shape[0], _ptr(s), k, _ptr(idx), _ptr(top)))
+        return idx, top
+
+    def top_k_raw(self, n, scores, k, top_index, top_score=None):
+        self._check(self.lib.adp_top_k(self.h, n, _ptr(scores), k, _ptr(top_index), _ptr(top_score)))
 
     def mutate(self, problem, seqs, positions, nucleotides):
         """≙ mutate_recursively for every (sequence, position, nucleotide) triple, applied on the device; returns the mutated

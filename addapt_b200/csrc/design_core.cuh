@@ -150,7 +150,7 @@ ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
 // set (and the score is meaningless) when a sequence holds letters outside ACGU/T.
 template <bool kFast, class E>
 ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint8_t* raw, DesignScratch& d, void* fold_small, double* mats,
-                              bool* declined = nullptr, double* dstate = nullptr) {
+                              bool* declined = nullptr, double* dstate = nullptr, double* qm_ext = nullptr) {
   double score = 0.;
   const int nT = sp.n_tot();
   for (int x = 0; x < sp.n_ctx; x++) {
@@ -182,9 +182,9 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
       }
       if constexpr (kFast) {
         #if defined(ADP_DESIGN_TWO_INST)
-        if (!run_pf_job_fast<E, false>(ex, job, fold_small, mats, dstate)) {
+        if (!run_pf_job_fast<E, false>(ex, job, fold_small, mats, dstate, qm_ext)) {
 #else
-        if (!run_pf_job_fast<E, true>(ex, job, fold_small, mats, dstate)) {
+        if (!run_pf_job_fast<E, true>(ex, job, fold_small, mats, dstate, qm_ext)) {
 #endif
           if (declined) *declined = true;
           return 0.;
@@ -261,7 +261,7 @@ struct McTrace {
 template <bool kFast, class E>
 ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTableDev& mv, uint64_t seed, uint64_t traj_id, int step0, int step1,
                           int thermo_kind, const double* thermo_args, DesignScratch& d, void* fold_small, double* mats, McState* st,
-                          double* dstate = nullptr, const McTrace* trace = nullptr) {
+                          double* dstate = nullptr, const McTrace* trace = nullptr, double* qm_ext = nullptr) {
   const int n = sp.n;
   const int nt_terms = sp.n_ctx * sp.n_tot();
   const bool tracing = trace && trace->interval > 0;
@@ -349,7 +349,7 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
       ex.sync();
       if (!changed) { oc2++; record(step, T, 2); continue; }                   // ACCEPT_UNCHANGED: not scored
     }
-    const double prop_s = score_construct<kFast>(ex, sp, d.prop, d, fold_small, mats, nullptr, dstate);
+    const double prop_s = score_construct<kFast>(ex, sp, d.prop, d, fold_small, mats, nullptr, dstate, qm_ext);
     if (start) { cur_s = best_s = last_prop = prop_s; continue; }
     const double diff = prop_s - cur_s;
     last_diff = diff;

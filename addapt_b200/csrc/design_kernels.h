@@ -63,5 +63,8 @@ LaunchPlan plan_design(const DeviceInfo&, int n_max, int jobs, bool fast, bool o
 cudaError_t launch_score(const ScoreBatchArgs&, const LaunchPlan&, bool fast, const PfTables* host_tables, cudaStream_t);
 cudaError_t launch_mc(const McArgs&, const LaunchPlan&, bool fast, const PfTables* host_tables, cudaStream_t);
 cudaError_t launch_mutate(const MutateArgs&, cudaStream_t);
+// the k (<= kTopKMax) best of n scores, best first, ties by lower index, NaN last: one CTA (radix select + bitonic sort)
+constexpr int kTopKMax = 1024;
+cudaError_t launch_top_k(const double* scores, int n, int k, int32_t* top_index, double* top_score, cudaStream_t);
 
 }  // namespace adp

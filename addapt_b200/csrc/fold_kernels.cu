@@ -10,7 +10,6 @@
 
 namespace adp {
 
-constexpr bool kQmGlobalDefault = false;     // see plan_pf_fast
 
 extern __shared__ __align__(16) unsigned char adp_smem[];
 
@@ -102,10 +101,10 @@ __device__ __forceinline__ PfJob make_pf_job(const PfBatchArgs& a, int jid) {
 
 // Fast path: one construct per CTA, level sums of the generic interior loops in registers (pf_fast.cuh).
 // kThreads = 256 serves n <= 128 with two CTAs per SM at 100 nt; 512 serves longer constructs.
-// kQmGlobal: Qb stays in shared memory, Qm moves to the CTA's slab of (L2-resident) global scratch, which makes room for a
-// third construct per SM at 100 nt (85 registers per thread).
+// kQmGlobal: Qb stays in shared memory, Qm moves to the CTA's slab of (L2-resident) global scratch: constructs of 101-128 nt, whose
+// two matrices leave room for one CTA per SM only, keep two CTAs per SM that way (plan_pf_fast).
 template <int kThreads, bool kSmemMats, bool kQmGlobal>
-__global__ void __launch_bounds__(kThreads, kThreads == 256 ? (kQmGlobal ? 3 : 2) : 1) pf_fast_kernel(const PfBatchArgs a) {
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) pf_fast_kernel(const PfBatchArgs a) {
   CtaExec<1> ex;
   const int n = a.n;
   const int jobs = a.B * a.V;
@@ -258,15 +257,16 @@ LaunchPlan plan_pf_fast(const DeviceInfo& d, int n, int jobs) {
   p.smem_bytes = p.mats_in_smem ? small_al + mats_bytes : small_al;
   size_t gdoubles = p.mats_in_smem ? 0 : fast_matrix_doubles(n);
   size_t by_threads = p.threads == 256 ? 2 : 1;            // __launch_bounds__ of pf_fast_kernel
-  // Qm in global scratch when that lets a third construct share the SM (group = 3 selects that kernel variant)
+  // Occupancy cliff above ~100 nt: two FP64 triangles + the vectors exceed half an SM's shared memory, i.e. ONE resident CTA (8 warps)
+  // per SM.  With Qm in the CTA's slab of L2-resident global scratch (group = 3 selects that kernel variant) the 256-thread kernel
+  // keeps two CTAs per SM up to 128 nt.  ADDAPT_B200_QM_GLOBAL=0 switches it off (measurements).
   const char* qmg = std::getenv("ADDAPT_B200_QM_GLOBAL");
-  const bool want_qmg = qmg ? std::atoi(qmg) != 0 : kQmGlobalDefault;
-  if (want_qmg && p.threads == 256 && p.mats_in_smem && d.smem_per_sm / (p.smem_bytes + 1024) < 3 &&
-      d.smem_per_sm / (small_al + qb_bytes + 1024) >= 3) {
+  const bool want_qmg = qmg ? std::atoi(qmg) != 0 : true;
+  if (want_qmg && p.threads == 256 && p.mats_in_smem && d.smem_per_sm / (p.smem_bytes + 1024) < 2 &&
+      d.smem_per_sm / (small_al + qb_bytes + 1024) >= 2) {
     p.group = 3;
     p.smem_bytes = small_al + qb_bytes;
     gdoubles = t4_count(n) + 2;
-    by_threads = 3;
   }
   p.gmat_stride = gdoubles + (n > fast_max_len(p.threads) ? fast_state_doubles(n) : 0);
   size_t per_sm = d.smem_per_sm / (p.smem_bytes + 1024);   // 1 KB reserved per resident CTA

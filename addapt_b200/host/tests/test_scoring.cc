@@ -375,7 +375,7 @@ GPU_TEST_CASE(gpu_batched_tsv, "BatchedMonteCarlo writes TsvTrajectoryReporter's
     CHECK(line == "#\tinitial_seq\t" + rhf_6->seq());
     std::getline(in, line);
     CHECK(line.rfind("step\tnum_steps\tcurrent_score\tproposed_score\tterm_weight[apo: not active]\tterm_value[apo: not active]\t", 0) == 0);
-    CHECK(line.size() > 30 && line.substr(line.size() - 26) == "current_seq\tproposed_seq\t");
+    CHECK(line.size() > 30 && line.substr(line.size() - 25) == "current_seq\tproposed_seq\t");
     int rows = 0;
     string last;
     while (std::getline(in, line)) { rows++; last = line; }

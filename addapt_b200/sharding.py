@@ -82,6 +82,38 @@ def gather_top_designs(scores, seqs, ids, k, dist=None, device=None, distinct=Fa
     return all_s[order], all_q[order], all_i[order]
 
 
+def gather_top_designs_device(engine, d_scores, d_seqs, id0, k, dist=None):
+    """The same exchange with the per-rank reduction ON THE DEVICE: `d_scores` [m] float64 and `d_seqs` [m, n] uint8 are torch
+    CUDA tensors holding this rank's trajectories (global ids id0 .. id0+m-1); the engine's top-k kernel (adp_top_k) picks the k
+    best, only those K records are all-gathered over NCCL, and the G*K gathered records are merged on the host.
+    Returns (scores [<=k], seqs [<=k, n], ids [<=k]) as numpy arrays, best first, identical on every rank."""
+    import torch
+    m, n = d_seqs.shape
+    kk = min(int(k), m)
+    idx = torch.empty(kk, dtype=torch.int32, device=d_scores.device)
+    top = torch.empty(kk, dtype=torch.float64, device=d_scores.device)
+    engine.top_k_raw(m, d_scores, kk, idx, top)                      # one kernel launch on the engine's stream, synchronised on return
+    s_t = torch.full((int(k),), float("-inf"), dtype=torch.float64, device=d_scores.device)
+    i_t = torch.full((int(k),), -1, dtype=torch.int64, device=d_scores.device)
+    q_t = torch.zeros((int(k), n), dtype=torch.uint8, device=d_scores.device)
+    s_t[:kk], i_t[:kk], q_t[:kk] = top, idx.long() + int(id0), d_seqs.index_select(0, idx.long())
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        world = dist.get_world_size()
+        S = [torch.empty_like(s_t) for _ in range(world)]
+        I = [torch.empty_like(i_t) for _ in range(world)]
+        Q = [torch.empty_like(q_t) for _ in range(world)]
+        dist.all_gather(S, s_t)
+        dist.all_gather(I, i_t)
+        dist.all_gather(Q, q_t)
+        s_t, i_t, q_t = torch.cat(S), torch.cat(I), torch.cat(Q)
+    all_s, all_i, all_q = s_t.cpu().numpy(), i_t.cpu().numpy(), q_t.cpu().numpy()
+    valid = all_i >= 0
+    all_s, all_i, all_q = all_s[valid], all_i[valid], all_q[valid]
+    key = np.where(np.isnan(all_s), -np.inf, all_s)
+    order = np.lexsort((all_i, np.isnan(all_s), -key))[:int(k)]      # best score first, NaN last, ties by global id
+    return all_s[order], all_q[order], all_i[order]
+
+
 def pick_best_scores(scores, window_size):
     """Peak picking over one trajectory's scores, as the reference's offline tools select designs from a TSV trajectory
     (reference tools/utils.py:36-51): repeatedly take the arg-max, record it, and blank +-window_size steps around it with the

@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_NT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mc-steps", type=int, default=100)
+    ap.add_argument("--no-mc-leg", action="store_true", help="skip the second timed leg (Monte-Carlo design run + top-K gather)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -333,7 +334,8 @@ def main():
     e2e_value = total_units / (ms_e2e * 1e-3)
     unit = {"fold_eval": "fold-evals/s", "sweep": "fold-evals/s", "mfe": "folds/s", "pf": "fills/s", "score": "scores/s", "mc": "MC steps/s"}[wl]
 
-    # ---- roofline of the dominant kernel (pf_batch_kernel: one launch per step) --------------------------
+    # ---- roofline of the dominant kernel (pf_fast_kernel: one launch per step) --------------------------
+    roofline = cpu = None
     if rank == 0:
         sample = host_seqs[:: max(1, B // 48)][:48]
         w = np.array([count_terms(r) for r in sample])
@@ -358,6 +360,36 @@ def main():
             v, cores, m, dt = cpu_port_rate(host_seqs[:4096])
             cpu = {"value": v, "unit": "fold-evals/s", "cores": cores, "kind": "port",
                    "sample": "first %d of this step's designs, apo+holo pf+bppm, %.1f s of CPU work on %d threads; oracle port (ViennaRNA libRNA is not in the image)" % (m, dt, cores)}
+    # ---- second timed leg (BASELINE.json configs[3], bounded): annealing Monte-Carlo trajectories of the rhf(6) design on every rank
+    #      (ids sharded by rank, no traffic inside the loop), then the one exchange step: per-rank top-K on the device (adp_top_k) and
+    #      an all_gather of the K records over NCCL
+    mc_leg = None
+    if wl == "fold_eval" and not args.no_mc_leg:
+        from addapt_b200.sharding import gather_top_designs_device
+        leg_traj, leg_steps, leg_k = 4096, 60, 1024
+        prob = Problem(RHF6, {"active": RHF6_ACTIVE}, [("active", "apo", False, 1.0), ("active", "holo", True, 1.0)], motif=THEO)
+        lb = torch.zeros(leg_traj, dtype=torch.float64, device=dev)
+        lq = torch.zeros(leg_traj, len(RHF6), dtype=torch.uint8, device=dev)
+        run = lambda: eng.mc_run_raw(prob, leg_traj, 2016, rank * leg_traj, leg_steps, ("annealing", 5.0, 0.0, 300), best_seq=lq, best_score=lb)
+        run()                                                         # warm-up
+        l0 = eng.launch_count()
+        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        barrier()
+        ea.record(stream)
+        run()
+        eb.record(stream)
+        top_s, top_q, top_i = gather_top_designs_device(eng, lb, lq, rank * leg_traj, leg_k, dist if world > 1 else None)
+        ec.record(stream)
+        barrier()
+        t = torch.tensor([ea.elapsed_time(eb), eb.elapsed_time(ec)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mc_ms, gather_ms = float(t[0].item()), float(t[1].item())
+        mc_leg = {"mc_steps_per_s": world * leg_traj * leg_steps / (mc_ms * 1e-3), "gather_ms": gather_ms, "top_k": int(top_s.shape[0]),
+                  "mc_config": "configs[3] bounded: %d annealing trajectories x %d steps per GPU of the 102-nt rhf(6) design, thermostat '5 to 0 in 300 steps'; "
+                               "per-rank top-%d on the device (adp_top_k), %s" % (leg_traj, leg_steps, leg_k, "all_gather of the K records over NCCL" if world > 1 else "single rank: no collective"),
+                  "mc_best_score": float(top_s[0]), "mc_gpu_launches": eng.launch_count() - l0}
+    if rank == 0:
         line = {
             "metric": METRIC if wl == "fold_eval" and n == N_NT else "%s (%s, %d nt)" % (unit, wl, n),
             "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -365,7 +397,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": "configs[2]: batched apo+holo McCaskill pf+bppm of 65,536 sgRNA-templated 100-nt designs per GPU" if wl == "fold_eval" and n == N_NT and B == BATCH else "%s B=%d n=%d" % (wl, B, n),
                        "designs_per_gpu_per_step": B, "n_nt": n, "l2": "256 MiB flush between timed iterations", "pair_queries": nq,
-                       "sharding": "independent designs per rank, no data-path collective"},
+                       "sharding": "independent designs per rank, no data-path collective",
+                       "energy_params": "%s (%s)" % (eng.param_provenance, os.path.basename(eng.param_file))},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": io[0], "d2h_bytes_per_step": io[1]},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
@@ -373,13 +406,14 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if mc_leg:
+            line.update(mc_leg)
         print(json.dumps(line))
     if wl == "mc":
         # the one exchange step of the design run: every rank's best designs, merged to a global top-K over NCCL
-        from addapt_b200.sharding import gather_top_designs
+        from addapt_b200.sharding import gather_top_designs_device
         t0 = time.perf_counter()
-        top_s, top_q, top_i = gather_top_designs(d_best.cpu().numpy(), d_bseq.cpu().numpy(), np.arange(rank * mc_traj, (rank + 1) * mc_traj),
-                                                 min(1024, mc_traj), dist if world > 1 else None, dev)
+        top_s, top_q, top_i = gather_top_designs_device(eng, d_best, d_bseq, rank * mc_traj, min(1024, mc_traj), dist if world > 1 else None)
         if rank == 0:
             print(json.dumps({"top_designs_gather": {"k": int(top_s.shape[0]), "ranks": world, "best_score": float(top_s[0]),
                                                      "best_seq": bytes(top_q[0]).decode(), "seconds": time.perf_counter() - t0}}), file=sys.stderr)

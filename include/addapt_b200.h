@@ -182,6 +182,12 @@ int adp_mc_run_trace(adp_engine *, const adp_problem *, int n_traj, uint64_t see
 int adp_mutate_batch(adp_engine *, const adp_problem *, int B, const uint8_t *seqs, const int32_t *positions,
                      const uint8_t *nucleotides, uint8_t *out_seqs, int32_t *freely_mutable);
 
+/* Per-rank reduction at the end of a sharded design run (the reference merges the TSV files of its N processes offline,
+ * tools/utils.py:27-51; here every rank keeps its k best trajectories and only those records cross NVLink): the k (<= 1024) best of
+ * n scores ON THE DEVICE, best first, ties by lower index, NaN last.  scores: n doubles (device memory in a run; host works too).
+ * top_index: min(k,n) int32 positions into scores; top_score: the same many doubles or NULL. */
+int adp_top_k(adp_engine *, int n, const double *scores, int k, int32_t *top_index, double *top_score);
+
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 /* Sustained FP64 FMA rate of this GPU (GFMA/s = 1e9 fused multiply-adds per second), measured with a
  * register-resident DFMA loop; the denominator of the SM-issue roofline in bench.py. */

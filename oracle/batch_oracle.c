@@ -35,7 +35,7 @@ static void *worker(void *arg) {
       if (J->kind == 0) rc = orc_pf(J->M, n, s, J->cst, J->mo, &J->dG[b], J->bppm ? J->bppm + (size_t)b * tsz : NULL);
       else if (J->kind == 1) { rc = orc_mfe(J->M, n, s, J->cst, J->mo, &J->e[b], st); if (J->structs) memcpy(J->structs + (size_t)b * n, st, n); }
       else {
-        int nt = J->P->n_terms * (J->P->n_ctx > 0 ? J->P->n_ctx : 1);
+        int nt = (J->P->n_terms + J->P->n_bp_terms) * (J->P->n_ctx > 0 ? J->P->n_ctx : 1);
         J->score[b] = orc_score(J->M, J->P, s, J->float_dg, J->terms ? J->terms + (size_t)b * nt : NULL);
       }
       if (rc) J->rc = rc;

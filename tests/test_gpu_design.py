@@ -127,3 +127,40 @@ def test_bp_terms_on_the_device(engine, oracle):
         o = oracle.mc_run(pr6.as_oracle_dict(), 3, t, 10, trace_interval=1)
         assert r["final_seq"][t] == o["final_seq"] and list(r["outcomes"][t]) == o["outcomes"]
         _check_trace((r["trace_values"][t], r["trace_seqs"][t]), (o["trace_values"], o["trace_seqs"]), pr6.n_term_values)
+
+
+def test_top_k_on_the_device(engine):
+    """adp_top_k against a host sort: best first, ties by lower index, -inf and NaN at the end, k > n, k = 1"""
+    from addapt_b200.sharding import local_top_k
+    rng = np.random.Generator(np.random.PCG64(8))
+    for n, k in ((65536, 1024), (5000, 1024), (1000, 16), (7, 1024), (1, 1), (4096, 1), (70000, 1000)):
+        s = np.round(rng.normal(size=n), 1)                     # rounded: many ties, also across the threshold
+        s[rng.integers(0, n, max(1, n // 50))] = -np.inf
+        idx, top = engine.top_k(s, k)
+        want = local_top_k(s, k)
+        assert np.array_equal(idx, want), (n, k)
+        assert np.array_equal(top, s[want])
+    s = rng.normal(size=1100)
+    s[::7] = np.nan
+    s[5] = s[6] = np.nanmax(s)
+    idx, top = engine.top_k(s, 1024)
+    fin = ~np.isnan(s)
+    want = [i for i in np.lexsort((np.arange(1100), -np.where(fin, s, -np.inf))) if fin[i]]
+    assert len(want) < 1024 and list(idx[:len(want)]) == want and np.isnan(top[len(want):]).all()
+    assert np.all(np.diff(idx[len(want):]) > 0)                 # the NaN tail in index order
+    assert list(engine.top_k(np.zeros(2000), 5)[0]) == [0, 1, 2, 3, 4]
+    assert list(engine.top_k(np.array([0.0, -0.0, 0.0]), 3)[0]) == [0, 1, 2]
+
+
+def test_gather_top_designs_on_the_device(engine):
+    """the design run's exchange step with the per-rank reduction on the device equals the host path"""
+    import torch
+    from addapt_b200.sharding import gather_top_designs, gather_top_designs_device
+    rng = np.random.Generator(np.random.PCG64(9))
+    m, n, k = 8192, 102, 1024
+    scores = np.round(rng.normal(size=m), 2)
+    seqs = rng.integers(65, 70, (m, n)).astype(np.uint8)
+    a = gather_top_designs(scores, seqs, np.arange(500, 500 + m), k)
+    b = gather_top_designs_device(engine, torch.from_numpy(scores).cuda(), torch.from_numpy(seqs).cuda(), 500, k)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

@@ -64,8 +64,8 @@ def _check_trace(a, b, n_terms):
     assert va.shape == vb.shape and np.array_equal(qa, qb)
     assert np.array_equal(va[:, 0], vb[:, 0]) and np.array_equal(va[:, 7], vb[:, 7])          # step, outcome
     assert np.array_equal(va[:, 6], vb[:, 6])                                                 # random threshold: bitwise (integer arithmetic)
-    np.testing.assert_allclose(va[:, 4], vb[:, 4], rtol=1e-12)         # temperature: the annealing schedule is bit-equal, the auto-scaling
-                                                                       # one divides by log(rate) of the device's math library
+    np.testing.assert_allclose(va[:, 4], vb[:, 4], rtol=1e-5)          # temperature: the annealing schedule is bit-equal (checked in
+                                                                       # test_gpu_parity), the auto-scaling one is a median of score differences
     for col in (1, 2, 3, 5) + tuple(range(8, 8 + n_terms)):
         fin = np.isfinite(vb[:, col])
         assert np.array_equal(np.isfinite(va[:, col]), fin)
