@@ -55,6 +55,9 @@ struct ScoreProblemDev {
   const int32_t* bp_qi;              // [n_ctx][n_bpq] contextual 0-based positions (device memory)
   const int32_t* bp_qj;
   const int32_t* bp_dpos;            // [n_ctx][n_bpd]
+  // Holo fills that are derived from their apo twin (fast path): twin[v] = index of the unconstrained / same-macrostate APO
+  // variant of a ligand-bound variant without outside pass, else -1; site_of[v] = 1 for an apo variant some holo variant derives from
+  int32_t twin[kMaxVariants], site_of[kMaxVariants];
   ADP_HD int n_tot() const { return n_terms + n_bp; }      // term values per context: macrostate terms, then bp terms
 };
 
@@ -117,7 +120,7 @@ ADP_HD double thermostat_T(int kind, const double* args, int step) {
 }
 
 // Shared-memory bytes a design CTA needs besides the fold working set.
-ADP_HD size_t design_extra_bytes(int n_max) { return 96 + (size_t)(n_max + 16) * 4 + (kMaxVariants + kMaxTerms * kMaxCtx + 8) * sizeof(double); }
+ADP_HD size_t design_extra_bytes(int n_max) { return 112 + (size_t)(n_max + 16) * 4 + (2 * kMaxVariants + kMaxTerms * kMaxCtx + 8) * sizeof(double); }
 
 struct DesignScratch {
   uint8_t* full;     // contextual sequence  [n_max+16]
@@ -127,6 +130,7 @@ struct DesignScratch {
   double* dg;        // [kMaxVariants]
   double* terms;     // [kMaxCtx*kMaxTerms]
   double* bcast;     // [8] broadcast slots
+  double* ratio;     // [kMaxVariants] Z_holo / Z_apo reported by the apo fills (PfJob::site_ratio)
   double* bp_out;    // [kMaxBp + kMaxDensPos] pair-query / paired-density results of the last fill (device memory; NULL without bp terms)
   double* train;     // [kMaxTrain] score differences the auto-scaling thermostat is trained on: the trajectory's slice of the
                      // device-memory window that is carried from launch to launch (NULL for the other thermostats); touched once a step
@@ -140,6 +144,7 @@ ADP_HD void carve_design(Carver& cv, DesignScratch& d, int n_max) {
   d.dg = cv.take<double>(kMaxVariants);
   d.terms = cv.take<double>(kMaxCtx * kMaxTerms);
   d.bcast = cv.take<double>(8);
+  d.ratio = cv.take<double>(kMaxVariants);
   d.bp_out = nullptr;     // set by the caller
   d.train = nullptr;      // set by the caller (not in shared memory: 4 KB that the fold working set needs)
 }
@@ -158,8 +163,22 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
     for (int p = ex.tid(); p < nx; p += ex.nthreads())
       d.full[p] = p < nb ? sp.before[x][p] : p < nb + sp.n ? raw[p - nb] : sp.after[x][p - nb - sp.n];
     ex.sync();
+    // Two rounds over the fills.  Round 0 folds every ensemble that has to be folded; an apo fill that a ligand-bound variant
+    // derives from also reports Z_holo / Z_apo (site mode of the outside pass: a fraction of a fill).  Round 1 completes the
+    // ligand-bound variants: dG_holo = dG_apo - kT ln(ratio), or a real fill when the motif occurs more than once (ratio = NaN).
+    for (int round = 0; round < (kFast ? 2 : 1); round++)
     for (int v = 0; v < sp.V; v++) {
       const VariantDev var = sp.variants[v];
+      const int twin = kFast ? sp.twin[v] : -1;
+      if (round == 0 && twin >= 0) continue;
+      if (round == 1) {
+        if (twin < 0) continue;
+        const double r = d.ratio[twin];
+        if (r == r) {
+          if (ex.tid() == 0) d.dg[v] = d.dg[twin] - sp.kT * log(r);
+          continue;
+        }
+      }
       PfJob job;
       job.seq = d.full;
       job.n = nx;
@@ -171,6 +190,7 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
       job.bppm = nullptr;
       job.n_query = 0;
       job.qi = nullptr; job.qj = nullptr; job.qprobs = nullptr;
+      if (kFast && sp.site_of[v] && !var.outside) { job.site_motif = sp.motif; job.site_ratio = d.ratio + v; }
       if (var.outside) {      // base-pair-probability terms read this fill's pair queries and paired densities
         job.n_query = sp.n_bpq;
         job.qi = sp.bp_qi + (size_t)x * sp.n_bpq;

@@ -26,6 +26,11 @@ struct PfJob {
   int n_dens = 0;               // positions (0-based) whose probability of being paired is wanted, answered into dens
   const int32_t* dens_pos = nullptr;
   double* dens = nullptr;
+  // Fast path, apo jobs only (motif == NULL): also report Z_holo / Z_apo for this ligand motif into *site_ratio -- 1 when the
+  // motif does not occur, 1 + (boltz - 1) P(plain hairpin at the site) when it occurs once (site mode of fast_outside: only the
+  // cells enclosing the site), NaN when it occurs more than once (the caller then folds the holo ensemble itself).
+  const MotifDev* site_motif = nullptr;
+  double* site_ratio = nullptr;
 };
 
 ADP_HD size_t pf_small_bytes(int n) { return sizeof(PfSmall) + 16 + ctx_bytes(n) + (size_t)9 * (n + 4) * sizeof(double); }
@@ -139,7 +144,7 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   if (ex.tid() == 0) w.counter[3] = 0;
   stage_hot(ex, H, job.T);
   for (int k = ex.tid(); k < w.ld; k += ex.nthreads()) w.vecp(kVEMLb)[k] = job.T->eMLb[k];
-  load_context(ex, c, job.seq, job.cst, job.motif);   // ends with a barrier
+  load_context(ex, c, job.seq, job.cst, job.motif ? job.motif : job.site_motif);   // ends with a barrier; marks the motif sites
   if (!fast_codes(ex, c, w)) w.counter[3] = 1;
   fast_special_hairpins(ex, c, job.T, w);
   ex.sync();
@@ -151,6 +156,35 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   const double Z = (kOneCstPath || c.has_cst) ? fast_inside<true>(ex, c, *H, job.T, mboltz, w) : fast_inside<false>(ex, c, *H, job.T, mboltz, w);
   if (ex.tid() == 0)
     *job.dG = Z > 0. ? (-log(Z) - n * log(job.T->pf_scale)) * job.T->kT / 1000. : (double)INFINITY;
+  if (job.site_ratio && job.site_motif && !job.motif) {
+    // Z_holo / Z_apo from the apo matrices (see FastOut): where does the motif occur?
+    const int mlen = job.site_motif->len;
+    if (ex.tid() == 0) {
+      int count = 0, at = 0;
+      for (int p = 1; p + mlen - 1 <= n; p++)
+        if (c.motif_at[p]) { count++; at = p; }
+      w.counter[0] = count;
+      w.counter[1] = at;
+      *job.site_ratio = count == 0 || !(Z > 0.) ? 1. : (double)NAN;      // no site, or an empty ensemble: nothing to reweight
+    }
+    ex.sync();
+    if (w.counter[0] == 1 && Z > 0.) {
+      const int at = w.counter[1];
+      ex.sync();                      // the counters are reused by the outside pass
+      FastOut site;
+      site.bppm = nullptr;
+      site.n_query = 0; site.qi = nullptr; site.qj = nullptr; site.qprobs = nullptr;
+      site.n_dens = 0; site.dens_pos = nullptr; site.dens = nullptr;
+      site.site_k = at;
+      site.site_l = at + mlen - 1;
+      site.site_ph = job.site_ratio;  // receives P(plain hairpin at the site) ...
+      if (kOneCstPath || c.has_cst) fast_outside<true>(ex, c, *H, job.T, nullptr, 1., w, site);
+      else fast_outside<false>(ex, c, *H, job.T, nullptr, 1., w, site);
+      if (ex.tid() == 0) *job.site_ratio = 1. + (job.site_motif->boltz - 1.) * *job.site_ratio;      // ... and is turned into the ratio
+      ex.sync();
+    }
+    return true;                      // site mode replaces the outside pass of the job
+  }
   if (!job.outside) return true;
   FastOut out;
   out.bppm = job.bppm;

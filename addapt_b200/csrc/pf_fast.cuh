@@ -892,6 +892,12 @@ struct FastOut {
   int n_dens;            // positions (0-based) whose probability of being paired is wanted
   const int32_t* dens_pos;
   double* dens;
+  // SITE MODE (site_k > 0): only the outside weights of the cells that enclose the pair (site_k, site_l) are evaluated -- rows
+  // k <= site_k, columns l >= site_l, which depend on nothing outside that corner -- and *site_ph receives the probability that
+  // (site_k, site_l) closes a plain hairpin loop.  With it the ligand-bound ensemble of a construct with ONE motif site follows
+  // from the apo fill:  Z_holo = Z_apo (1 + (boltz - 1) P_h), because binding only reweights the structures that hold that hairpin.
+  int site_k = 0, site_l = 0;
+  double* site_ph = nullptr;
 };
 
 ADP_HD size_t bppm_index(int n, int i, int j) {      // 1-based i <= j
@@ -938,20 +944,43 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   const double invZ = 1. / Z;
   const double s1 = H.scale1, eb1 = H.eMLb1;
   const bool has_motif = motif && motif->len > 0;
+  const bool site_mode = out.site_k > 0;
+  const int row_max = site_mode ? out.site_k : n;          // rows / columns that are evaluated at all
+  const int l_min = site_mode ? out.site_l : kTurn + 1;
+  if (site_mode) {
+    // the exterior suffix Q(l,n) right of the site, which the full pass accumulates from rows that are skipped here: position l
+    // unpaired, or paired with some l' (one warp, a row of Qb per step)
+    ex.sync();
+    if (ex.warp() == 0) {
+      for (int l = n; l > out.site_l; l--) {
+        double e = 0.;
+        const int cpl = cp[l], sl = c.S[l];
+        ADP_NOUNROLL
+        for (int j = l + kTurn + 1 + ex.lane(); j <= n; j += E::kWarp) {
+          const double v = qb[t4(l, j)];
+          if (v != 0.) {
+            const double plain = (l > 1 && j < n) ? v * H.RI[(cn[j] << 4) | cpl] : v;
+            e += plain * fast_stem_ext(c, H, pair_type(sl, c.S[j]), l, j) * qln[j + 1];
+          }
+        }
+        e = ex.warp_sum(e);
+        if (ex.lane() == 0) qln[l] = ((!kCst || can_unpair(c, l)) ? qln[l + 1] * s1 : 0.) + e;
+        ex.warp_sync();
+      }
+    }
+    if (tid == 0) *out.site_ph = 0.;
+    ex.sync();
+  }
 
   // multiloop carrier A(., ln) for every possible 5' closing position i <= ln-5: rows from a queue, a warp-sized chunk at a time
   auto carriers = [&](int ln) {
-    const int nrow = ln - 5;
+    const int nrow = ln - 5 < row_max - 1 ? ln - 5 : row_max - 1;      // rows a listed cell can read: i < k <= row_max
 #if defined(ADP_X_OUT_NOCARRIER)
     if (true) return;
 #endif
     if (ln >= n || nrow < 1) return;
     double* const vA = w.vecp(kOA + (ln & 1));
-#if defined(ADP_CARRIER_LG)
-    const int lg = E::kSerial ? 0 : ADP_CARRIER_LG;
-#else
-    const int lg = E::kSerial ? 0 : group_lg(nrow, nt_lg, warp_lg);
-#endif
+    const int lg = E::kSerial ? 0 : group_lg(nrow, nt_lg, warp_lg);      // rows fill the CTA once (1, 2, 4 and 8 lanes per row measured: all slower)
     const int Ga = 1 << lg, per = E::kWarp >> lg, subA = ex.lane() & (Ga - 1);
     const int gstep = (Ga * (Ga - 1)) >> 1;
     const int nchunk = (nrow + per - 1) / per;
@@ -998,7 +1027,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
       if (key < ln + 1) key += R;
       const int k = key - ln;
-      if (k >= 1 && k <= nr) {
+      if (k >= 1 && k <= nr && k <= row_max) {
         int sm = (k - 2) + (n - ln - 1);            // u1 <= k-2, u2 <= n-ln-1
         if (sm > kMaxLoop) sm = kMaxLoop;
         sm -= par;                                  // level Q is on iff 4 + 2Q <= sm
@@ -1049,7 +1078,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     ADP_NOUNROLL
     for (int r = nt - 1 - tid; r < nr; r += nt) {
       const int k = r + 1;
-      const bool on = col[k] != 0.;
+      const bool on = k <= row_max && col[k] != 0.;
       iscell[k] = on;
       if (on) cells[ex.atomic_inc(counter)] = (uint16_t)k;
     }
@@ -1109,7 +1138,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   ADP_TICK(1)
   // l = n+1 is a warm-up turn without cells: it only prepares column n; l = 4 is a run-out turn: it writes the results of
   // column 5 (one call site of every piece keeps the code small)
-  for (int l = n + 1; l >= kTurn + 1; l--) {
+  for (int l = n + 1; l >= l_min; l--) {
     const int m = l <= n ? w.counter[l % 3] : 0;
     if (tid == 0) { w.counter[(l + 1) % 3] = 0; w.qctr[(l + 1) % 3] = 0; }      // the slots of phase l-2 (nobody reads them in this phase)
     ADP_NOUNROLL
@@ -1119,8 +1148,9 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       const int j = l + S - 3;
       w.lvoff[((l & 1) << 5) + t] = (((j - 4) * (j - 5)) >> 1) * (int)sizeof(double);
     }
+    const bool more = l > kTurn + 2 && l > l_min;      // another column follows
 #if !defined(ADP_LEVELS_LAST)
-    if (l > kTurn + 2) levels(l - 1);      // first, by every warp at the same time (see the inside pass)
+    if (more) levels(l - 1);      // first, by every warp at the same time (see the inside pass)
 #endif
     // ---- cells(l): outside weight of every listed pair (k,l)
     if (m > 0) {
@@ -1249,6 +1279,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           pcol[k] = val * qbv;
           accq[k] += qbv * sx * qln[l + 1];
           if (has_motif && is_motif_site(c, k, l)) pm[k] = val * fast_hairpin<kCst>(c, H, G, w, motif_boltz, k, l, type);
+          if (site_mode && k == out.site_k && l == out.site_l) *out.site_ph = val * fast_hairpin<kCst>(c, H, G, w, 1., k, l, type);
           const int code = (cn[k] << 4) | cpl;             // outer orientation
           const double pre = val * H.FI[code];             // outside weight, premultiplied
           qb[idx] = pre;
@@ -1262,16 +1293,16 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     ADP_TICK(0)
     // ---- everything else of the phase
 #if defined(ADP_LEVELS_LAST)
-    if (l > kTurn + 2) levels(l - 1);
+    if (more) levels(l - 1);
 #endif
     ADP_TICK(4)
-    if (l > kTurn + 2) list_rows(l - 1);
+    if (more) list_rows(l - 1);
     if (l <= n && l > kTurn + 1) rest_rows(l);
-    if (l <= n - 1) results(l + 1);
+    if (l <= n - 1 && !site_mode) results(l + 1);
     // exterior suffix Q(l-1,n): position l-1 unpaired, or paired with some l' >= l+3 (already accumulated)
-    if (l > kTurn + 2 && tid == nt - 1) qln[l - 1] = ((!kCst || can_unpair(c, l - 1)) ? qln[l] * s1 : 0.) + accq[l - 1];
+    if (more && !site_mode && tid == nt - 1) qln[l - 1] = ((!kCst || can_unpair(c, l - 1)) ? qln[l] * s1 : 0.) + accq[l - 1];
     ADP_TICK(5)
-    if (l > kTurn + 2) carriers(l - 1);
+    if (more) carriers(l - 1);
     ADP_TICK(6)
     ex.sync();
     ADP_TICK(7)
@@ -1279,7 +1310,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
 
   // the motif's inner pairs inherit the probability of the bound hairpin
   ex.sync();
-  if (has_motif && tid == 0) {
+  if (has_motif && !site_mode && tid == 0) {
     for (int i = 1; i + motif->len - 1 <= n; i++) {
       if (!c.motif_at[i] || pm[i] == 0.) continue;
       for (int q = 0; q < motif->n_pairs; q++) {

@@ -113,6 +113,24 @@ inline void compile_problem(const adp_problem& pr, double kT_kcal, CompiledProbl
       throw std::string("base-pair-probability term kind must be 0 (pair) or 1 (density)");
     }
   }
+  // ligand-bound fills without outside pass derive from their apo twin (fold_jobs.cuh, PfJob::site_ratio); an apo twin that has an
+  // outside pass of its own (bp terms) cannot report the ratio, so its holo variant is folded
+  for (int v = 0; v < kMaxVariants; v++) { sp.twin[v] = -1; sp.site_of[v] = 0; }
+  const int V0 = sp.V;
+  for (int v = 0; v < V0; v++) {
+    if (!sp.variants[v].use_motif || sp.variants[v].outside) continue;
+    int u = -1;
+    for (int k = 0; k < sp.V; k++)
+      if (!sp.variants[k].use_motif && sp.variants[k].cst_id == sp.variants[v].cst_id) u = k;
+    if (u < 0) {
+      if (sp.V >= kMaxVariants) continue;             // no room for the twin: fold the holo ensemble itself
+      sp.variants[sp.V] = VariantDev{sp.variants[v].cst_id, 0, 0, 0};
+      u = sp.V++;
+    }
+    if (sp.variants[u].outside) continue;
+    sp.twin[v] = u;
+    sp.site_of[u] = 1;
+  }
   sp.n_bpq = (int)qi.size();
   sp.n_bpd = (int)dpos.size();
   for (int x = 0; x < sp.n_ctx; x++) {

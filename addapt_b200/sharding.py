@@ -5,7 +5,35 @@ In the reference, parallelism is N independent OS processes with different seeds
 (reference data/20160705_production_run_favor_wt/production_run.sh:5-8, tools/utils.py:27-51).  Here trajectory t draws from
 Philox keyed by (seed, t), so any partition of the ids over ranks gives the same trajectories, and the merge is one
 all_gather of K fixed-size records per rank (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+import os
+import sys
+
 import numpy as np
+
+
+def nccl_log_begin(world):
+    """Keep NCCL's communicator log as evidence without polluting stdout (which carries result lines): NCCL_DEBUG=INFO / INIT
+    into a per-process file that nccl_log_end() copies to stderr.  (NCCL_DEBUG_FILE=/dev/stderr re-opens the descriptor and
+    truncates a redirected stderr file.)  A caller's own NCCL_DEBUG / NCCL_DEBUG_FILE are respected.  Call before importing torch."""
+    if world <= 1:
+        return None
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    if "NCCL_DEBUG_FILE" in os.environ:
+        return None
+    path = "/tmp/addapt_b200_nccl_%d.log" % os.getpid()
+    os.environ["NCCL_DEBUG_FILE"] = path
+    return path
+
+
+def nccl_log_end(path):
+    if not path or not os.path.exists(path):
+        return
+    with open(path) as f:
+        for line in f:
+            sys.stderr.write(line)
+    sys.stderr.flush()
+    os.unlink(path)
 
 
 def shard_range(n_units, rank, world):

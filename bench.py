@@ -205,19 +205,17 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries ONE JSON line, so NCCL's log goes to stderr -- it is NOT switched off: the communicator lines
+    # ("... rank R nranks N ...") are the record that N ranks really formed one communicator.  A caller's NCCL_DEBUG /
+    # NCCL_DEBUG_FILE are respected; the default is INFO restricted to the INIT subsystem.  Set before torch is imported.
+    from addapt_b200.sharding import nccl_log_begin, nccl_log_end
+    nccl_log = nccl_log_begin(world)
     import torch
     import torch.distributed as dist
     import addapt_b200
     from addapt_b200.capi import Problem
 
     torch.cuda.set_device(local)
-    # stdout carries ONE JSON line, so NCCL's log goes to stderr -- it is NOT switched off: the communicator lines
-    # ("... rank R nranks N ...") are the record that N ranks really formed one communicator.  A caller's NCCL_DEBUG /
-    # NCCL_DEBUG_FILE are respected; the default is INFO restricted to the INIT subsystem.
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = addapt_b200.Engine(local)          # raises without the CUDA library / device: no fallback
@@ -371,7 +369,8 @@ def main():
         lb = torch.zeros(leg_traj, dtype=torch.float64, device=dev)
         lq = torch.zeros(leg_traj, len(RHF6), dtype=torch.uint8, device=dev)
         run = lambda: eng.mc_run_raw(prob, leg_traj, 2016, rank * leg_traj, leg_steps, ("annealing", 5.0, 0.0, 300), best_seq=lq, best_score=lb)
-        run()                                                         # warm-up
+        run()                                                         # warm-up of the kernel ...
+        gather_top_designs_device(eng, lb, lq, rank * leg_traj, leg_k, dist if world > 1 else None)     # ... and of the exchange (lazy module loads, NCCL channels)
         l0 = eng.launch_count()
         ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         barrier()
@@ -420,6 +419,7 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    nccl_log_end(nccl_log)
     eng.close()
 
 

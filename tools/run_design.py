@@ -28,14 +28,12 @@ def main():
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    if world > 1:      # NCCL's communicator lines are evidence, not noise: keep them, on stderr (stdout carries the JSON line)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    from addapt_b200.sharding import nccl_log_begin, nccl_log_end      # NCCL's communicator lines are evidence: kept, on stderr
+    nccl_log = nccl_log_begin(world)
     import torch
     import torch.distributed as dist
     import addapt_b200
-    from addapt_b200.sharding import gather_top_designs, shard_range
+    from addapt_b200.sharding import gather_top_designs, gather_top_designs_device, shard_range
     from tests import cases
 
     torch.cuda.set_device(local)
@@ -51,17 +49,25 @@ def main():
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    r = eng.mc_run(problem, b - a, args.seed, args.steps, thermostat=thermo, traj_id0=a)
+    # sequences, scores and outcome counters stay on the device: the run's only exchange is the top-K gather below
+    m, n = b - a, problem.n
+    dev = torch.device("cuda", local)
+    d_best_seq = torch.zeros(m, n, dtype=torch.uint8, device=dev)
+    d_best = torch.zeros(m, dtype=torch.float64, device=dev)
+    d_oc = torch.zeros(m, 4, dtype=torch.int32, device=dev)
+    eng.mc_run_raw(problem, m, args.seed, a, args.steps, thermo, best_seq=d_best_seq, best_score=d_best, outcomes=d_oc)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    oc = torch.tensor(r["outcomes"].sum(axis=0).astype(np.int64), device="cuda")
+    oc = d_oc.to(torch.int64).sum(dim=0)
     tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(oc)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    seqs = np.frombuffer("".join(r["best_seq"]).encode(), dtype=np.uint8).reshape(b - a, -1)
     tg = time.perf_counter()
-    top_s, top_q, top_i = gather_top_designs(r["best_score"], seqs, np.arange(a, b), args.topk, dist if world > 1 else None, torch.device("cuda", local), distinct=args.distinct)
+    if args.distinct:      # ranking distinct designs needs every trajectory's sequence: host path
+        top_s, top_q, top_i = gather_top_designs(d_best.cpu().numpy(), d_best_seq.cpu().numpy(), np.arange(a, b), args.topk, dist if world > 1 else None, dev, distinct=True)
+    else:                  # per-rank top-K on the device (adp_top_k), K records over NCCL
+        top_s, top_q, top_i = gather_top_designs_device(eng, d_best, d_best_seq, a, args.topk, dist if world > 1 else None)
     tg = time.perf_counter() - tg
     if rank == 0:
         top_seqs = [bytes(q).decode() for q in top_q]
@@ -70,7 +76,8 @@ def main():
         oc = oc.cpu().numpy()
         total = int(oc.sum())
         out = {"config": "configs[3]: %d trajectories x %d steps, thermostat '%s', seed %d" % (args.traj, args.steps, args.thermostat, args.seed),
-               "n_gpus": world, "seconds": float(tmax.item()), "mc_steps_per_s": args.traj * args.steps / float(tmax.item()),
+               "n_gpus": world, "seconds": float(tmax.item()), "energy_params": eng.param_provenance,
+               "exchange": "per-rank top-K on the device (adp_top_k) + all_gather of K records over NCCL" if not args.distinct else "host merge of distinct designs", "mc_steps_per_s": args.traj * args.steps / float(tmax.item()),
                "outcomes": dict(zip(["REJECT", "ACCEPT_WORSENED", "ACCEPT_UNCHANGED", "ACCEPT_IMPROVED"], [int(x) for x in oc])),
                "outcome_fractions": [round(float(x) / max(total, 1), 4) for x in oc],
                "start_score": start_score, "top_k": int(top_s.shape[0]), "gather_seconds": tg,
@@ -84,6 +91,7 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    nccl_log_end(nccl_log)
     eng.close()
 
 
