@@ -253,6 +253,7 @@ struct McState {
   double cur_score, best_score;
   double T_auto, last_diff;          // auto-scaling thermostat: current temperature, most recent score difference
   double last_prop, last_crit, last_u;   // trajectory records: proposed score, Metropolis criterion and threshold of the last SCORED step
+  double step_T, step_u;                 // temperature and acceptance threshold of the step being scored (parked here across the fold)
   int32_t best_step, ntrain;         // best_step = -1: the start sequence; ntrain: filled part of the training window
   uint32_t outcomes[4];              // REJECT, ACCEPT_WORSENED, ACCEPT_UNCHANGED, ACCEPT_IMPROVED
 };
@@ -285,26 +286,21 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
   const int n = sp.n;
   const int nt_terms = sp.n_ctx * sp.n_tot();
   const bool tracing = trace && trace->interval > 0;
-  double last_prop, last_crit, last_u;
-  double cur_s, best_s, T_auto, last_diff;
-  int best_step, ntrain;
-  uint32_t oc0, oc1, oc2, oc3;
+  // The trajectory's scalars stay in *st (shared memory), not in registers: they are live across the fold, where every register
+  // counts (with them in registers the kernel spilled 18 doubles and a Monte-Carlo step scored 29 % slower than a batch score
+  // of the same sequence).  Thread 0 writes them; a barrier at the top of every step publishes the writes.
   if (step0 == 0) {
     // the start sequence is scored by the loop below as "step -1" (one call site of the fold code keeps the kernel small)
-    cur_s = best_s = 0.;
-    best_step = -1;
-    oc0 = oc1 = oc2 = oc3 = 0;
-    ntrain = 0;
-    T_auto = thermo_kind == 2 ? thermo_args[2] : 0.;
-    last_diff = 0.;
-    last_prop = last_crit = last_u = 0.;
-  } else {
-    cur_s = st->cur_score; best_s = st->best_score; best_step = st->best_step;
-    oc0 = st->outcomes[0]; oc1 = st->outcomes[1]; oc2 = st->outcomes[2]; oc3 = st->outcomes[3];
-    ntrain = st->ntrain; T_auto = st->T_auto; last_diff = st->last_diff;
-    last_prop = st->last_prop; last_crit = st->last_crit; last_u = st->last_u;
-    if (tracing)
-      for (int t = ex.tid(); t < nt_terms; t += ex.nthreads()) d.terms[t] = trace->terms_state[t];
+    if (ex.tid() == 0) {
+      st->cur_score = st->best_score = 0.;
+      st->best_step = -1;
+      st->outcomes[0] = st->outcomes[1] = st->outcomes[2] = st->outcomes[3] = 0;
+      st->ntrain = 0;
+      st->T_auto = thermo_kind == 2 ? thermo_args[2] : 0.;
+      st->last_diff = st->last_prop = st->last_crit = st->last_u = 0.;
+    }
+  } else if (tracing) {
+    for (int t = ex.tid(); t < nt_terms; t += ex.nthreads()) d.terms[t] = trace->terms_state[t];
   }
   ex.sync();
   // one record, after the decision of `step` (collective; see McTrace)
@@ -315,7 +311,7 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
     double* v = trace->vals + (size_t)r * (kTraceScalars + nt_terms);
     uint8_t* q = trace->seqs + (size_t)r * 2 * n;
     if (ex.tid() == 0) {
-      v[0] = step; v[1] = cur_s; v[2] = last_prop; v[3] = last_diff; v[4] = T; v[5] = last_crit; v[6] = last_u; v[7] = outcome;
+      v[0] = step; v[1] = st->cur_score; v[2] = st->last_prop; v[3] = st->last_diff; v[4] = T; v[5] = st->last_crit; v[6] = st->last_u; v[7] = outcome;
     }
     for (int t = ex.tid(); t < nt_terms; t += ex.nthreads()) v[kTraceScalars + t] = d.terms[t];
     for (int p = ex.tid(); p < n; p += ex.nthreads()) { q[p] = d.cur[p]; q[n + p] = d.prop[p]; }
@@ -327,6 +323,7 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
   const int period = thermo_kind == 2 ? (int)thermo_args[1] : 0;
   for (int step = step0 == 0 ? -1 : step0; step < step1 && (step < 0 || mv.n_free > 0); step++) {
     const bool start = step < 0;          // score the start sequence: proposal = current, always "accepted", not counted
+    ex.sync();                            // thread 0's updates of *st in the previous step are visible from here on
     double T = 0., u = 0.;
     if (start) {
       for (int p = ex.tid(); p < n; p += ex.nthreads()) { d.prop[p] = d.cur[p]; d.best[p] = d.cur[p]; }
@@ -334,8 +331,9 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
     } else {
       T = thermostat_T(thermo_kind, thermo_args, step);
       if (thermo_kind == 2) {
-        if (ex.tid() == 0) d.train[ntrain] = last_diff;
-        ntrain++;
+        const int ntrain = st->ntrain + 1;
+        ex.sync();                        // everyone has read the count before thread 0 advances it
+        if (ex.tid() == 0) { d.train[ntrain - 1] = st->last_diff; st->ntrain = ntrain; }
         if (ntrain >= period) {
           ex.sync();
           const int mid = ntrain / 2;
@@ -349,12 +347,14 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
             if (rank == mid) d.bcast[0] = va;
           }
           ex.sync();
-          const double t = d.bcast[0] / log(thermo_args[0]);
-          T_auto = t > 0. ? t : 0.;
-          ntrain = 0;
-          ex.sync();
+          if (ex.tid() == 0) {
+            const double t = d.bcast[0] / log(thermo_args[0]);
+            st->T_auto = t > 0. ? t : 0.;
+            st->ntrain = 0;
+          }
         }
-        T = T_auto;
+        ex.sync();
+        T = st->T_auto;
       }
       uint32_t r[4];
       philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, 0u, (uint32_t)traj_id, (uint32_t)(traj_id >> 32), r);
@@ -367,33 +367,42 @@ ADP_HD void mc_trajectory(const E& ex, const ScoreProblemDev& sp, const MoveTabl
       const bool changed = closure_changes(mv, slot, nt, d.cur);
       if (ex.tid() == 0) apply_closure(mv, slot, nt, d.prop);
       ex.sync();
-      if (!changed) { oc2++; record(step, T, 2); continue; }                   // ACCEPT_UNCHANGED: not scored
+      if (!changed) {                                                          // ACCEPT_UNCHANGED: not scored
+        if (ex.tid() == 0) st->outcomes[2]++;
+        record(step, T, 2);
+        continue;
+      }
+      if (ex.tid() == 0) { st->step_T = T; st->step_u = u; }                   // parked in shared memory across the fold
     }
     const double prop_s = score_construct<kFast>(ex, sp, d.prop, d, fold_small, mats, nullptr, dstate, qm_ext);
-    if (start) { cur_s = best_s = last_prop = prop_s; continue; }
-    const double diff = prop_s - cur_s;
-    last_diff = diff;
-    const double crit = exp(diff / T);
-    last_prop = prop_s; last_crit = crit; last_u = u;
-    if (crit < u) { oc0++; record(step, T, 0); continue; }                     // REJECT (NaN compares false: accept)
-    if (diff > 0) oc3++; else oc1++;
-    for (int p = ex.tid(); p < n; p += ex.nthreads()) d.cur[p] = d.prop[p];
-    cur_s = prop_s;
-    if (cur_s > best_s) {
-      best_s = cur_s;
-      best_step = step;
-      for (int p = ex.tid(); p < n; p += ex.nthreads()) d.best[p] = d.prop[p];
+    if (start) {
+      if (ex.tid() == 0) st->cur_score = st->best_score = st->last_prop = prop_s;
+      continue;
     }
+    T = st->step_T;
+    u = st->step_u;
+    const double cur_s = st->cur_score, best_s = st->best_score;
+    const double diff = prop_s - cur_s;
+    const double crit = exp(diff / T);
+    const bool reject = crit < u;                                              // NaN compares false: accept
+    ex.sync();                                                                 // everyone has read the scores
+    if (ex.tid() == 0) {
+      st->last_diff = diff; st->last_prop = prop_s; st->last_crit = crit; st->last_u = u;
+      if (reject) st->outcomes[0]++;
+      else {
+        st->outcomes[diff > 0 ? 3 : 1]++;
+        st->cur_score = prop_s;
+        if (prop_s > best_s) { st->best_score = prop_s; st->best_step = step; }
+      }
+    }
+    if (reject) { ex.sync(); record(step, T, 0); continue; }
+    for (int p = ex.tid(); p < n; p += ex.nthreads()) d.cur[p] = d.prop[p];
+    if (prop_s > best_s)
+      for (int p = ex.tid(); p < n; p += ex.nthreads()) d.best[p] = d.prop[p];
     ex.sync();
     record(step, T, diff > 0 ? 3 : 1);
   }
   ex.sync();
-  if (ex.tid() == 0) {
-    st->cur_score = cur_s; st->best_score = best_s; st->best_step = best_step;
-    st->outcomes[0] = oc0; st->outcomes[1] = oc1; st->outcomes[2] = oc2; st->outcomes[3] = oc3;
-    st->ntrain = ntrain; st->T_auto = T_auto; st->last_diff = last_diff;
-    st->last_prop = last_prop; st->last_crit = last_crit; st->last_u = last_u;
-  }
   if (tracing)
     for (int t = ex.tid(); t < nt_terms; t += ex.nthreads()) trace->terms_state[t] = d.terms[t];
   ex.sync();

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
   CtaExec<G> ex;
   DesignSmem s = carve_design_smem<kFast, kSmemMats, kQmGlobal>(a.sp.n_max, a.gmats, a.gmat_stride);
   __shared__ McState st;
+  __shared__ McTrace tr;
   const int n = a.sp.n;
   s.d.bp_out = a.bp_out ? a.bp_out + (size_t)blockIdx.x * (kMaxBp + kMaxDensPos) : nullptr;
   for (int t = blockIdx.x; t < a.n_traj; t += gridDim.x) {
@@ -79,14 +80,15 @@ __global__ void __launch_bounds__(512) mc_kernel(const McArgs a) {
       if (threadIdx.x == 0) st = a.state[t];
     }
     s.d.train = a.train_state ? a.train_state + (size_t)t * a.train_stride : nullptr;     // the training window stays in device memory
-    McTrace tr;
-    tr.interval = a.trace_interval;
-    tr.cap = a.trace_cap;
-    if (a.trace_interval > 0) {
-      const int nt_terms = a.sp.n_ctx * a.sp.n_tot();
-      tr.vals = a.trace_vals + (size_t)t * a.trace_cap * (kTraceScalars + nt_terms);
-      tr.seqs = a.trace_seqs + (size_t)t * a.trace_cap * 2 * n;
-      tr.terms_state = a.trace_terms_state + (size_t)t * nt_terms;
+    if (threadIdx.x == 0) {            // in shared memory like the rest of the trajectory's state: registers are for the fold
+      tr.interval = a.trace_interval;
+      tr.cap = a.trace_cap;
+      if (a.trace_interval > 0) {
+        const int nt_terms = a.sp.n_ctx * a.sp.n_tot();
+        tr.vals = a.trace_vals + (size_t)t * a.trace_cap * (kTraceScalars + nt_terms);
+        tr.seqs = a.trace_seqs + (size_t)t * a.trace_cap * 2 * n;
+        tr.terms_state = a.trace_terms_state + (size_t)t * nt_terms;
+      }
     }
     __syncthreads();
     mc_trajectory<kFast>(ex, a.sp, *a.moves, a.seed, a.traj_id0 + (uint64_t)t, a.step0, a.step1, a.thermo_kind, a.thermo_args, s.d, s.fold_small,
