@@ -13,12 +13,13 @@ import numpy as np
 
 def nccl_log_begin(world):
     """Keep NCCL's communicator log as evidence without polluting stdout (which carries result lines): NCCL_DEBUG=INFO / INIT
-    into a per-process file that nccl_log_end() copies to stderr.  (NCCL_DEBUG_FILE=/dev/stderr re-opens the descriptor and
+    (raised from VERSION / WARN if that is what the environment says) into a per-process file that nccl_log_end() copies to stderr.  (NCCL_DEBUG_FILE=/dev/stderr re-opens the descriptor and
     truncates a redirected stderr file.)  A caller's own NCCL_DEBUG / NCCL_DEBUG_FILE are respected.  Call before importing torch."""
     if world <= 1:
         return None
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):      # quieter than INFO (the pool's boxes export VERSION)
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     if "NCCL_DEBUG_FILE" in os.environ:
         return None
     path = "/tmp/addapt_b200_nccl_%d.log" % os.getpid()
