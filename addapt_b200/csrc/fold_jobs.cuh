@@ -261,7 +261,7 @@ ADP_HD bool run_mfe_job_fast(const E& ex, const MfeJob& job, void* small, int32_
   carve_ctx(cv, c, n);
   MfeFastWork w;
   w.ld = fast_ld(n);
-  w.R = fast_R(n);
+  w.R = mfe_fast_R(n);
   w.vbase = cv.take<int32_t>((size_t)kMfeFastVectors * w.ld);
   w.cn = cv.take<uint8_t>(w.ld);
   w.cp = cv.take<uint8_t>(w.ld);

@@ -322,14 +322,14 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
     const int32_t* fm1_prev = w.vecp((jn - 1) & 1);
     int32_t* fm1_cur = w.vecp(jn & 1);
     int* counter = w.counter + (jn & 1);
+    const int kbase = ((jn + 1) / R) * R;
     for (int task = tid; task < 2 * half; task += nt) {
       const int par = task >= half ? 1 : 0;
-      int key = task - par * half;
-      if (key >= R) continue;
+      const int slot = task - par * half;
+      if (slot >= R) continue;
       if (mem_state)
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
-      if (key < jn + 1) key += R;
-      const int i = key - jn;
+      const int i = fast_slot_key(slot, kbase, jn, R) - jn;
       if (i >= 1 && i <= nr) {
         int sm = jn - i - 6;
         if (sm > kMaxLoop) sm = kMaxLoop;

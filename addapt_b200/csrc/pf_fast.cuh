@@ -237,7 +237,14 @@ struct FastWork {
 ADP_HD int t4(int i, int j) { return (((j - 4) * (j - 5)) >> 1) + (i - 1); }
 ADP_HD size_t t4_count(int n) { return n >= 5 ? (size_t)(n - 4) * (n - 3) / 2 : 0; }
 ADP_HD int fast_ld(int n) { return (n + 6) & ~1; }
-ADP_HD int fast_R(int n) { return n < 4 ? 4 : n; }      // anti-diagonal keys i+j <= 2n-4 < 2R, live window < R
+// Anti-diagonal slots: at column j the live anti-diagonals are the keys i+j of the rows i = 1 .. j-4, a window of at most n-4
+// consecutive keys, so any R >= n-4 slots (key mod R) never collide.  R = n-4 packs the level tasks of a 100-nt construct into
+// exactly three warps per parity; measured on one box (round 2): inside fills +2.7 %, MFE folds +3.3 %, but fold-evals -0.3 %,
+// scores -3 % and Monte-Carlo steps -5.5 % -- so the PF kernels keep R = n and the MFE kernel (mfe_fast_R) takes n-4.
+ADP_HD int fast_R(int n) { return n < 4 ? 4 : n; }
+ADP_HD int mfe_fast_R(int n) { return n < 8 ? 4 : n - 4; }
+// the live key of `slot` at column j: the only key in [j+1, j+R] congruent to the slot; kbase = ((j+1)/R)*R
+ADP_HD int fast_slot_key(int slot, int kbase, int j, int R) { const int key = kbase + slot; return key < j + 1 ? key + R : key; }
 ADP_HD int fast_max_len(int threads) { return threads / 2; }      // longest construct with register-resident level sums
 ADP_HD size_t fast_state_doubles(int n) { return (size_t)2 * fast_R(n) * kFastLevels; }
 
@@ -512,14 +519,14 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     double* const gen0 = w.vecp(kVGen0 + (jn & 1));
     double* const gen1 = w.vecp(kVGen1 + (jn & 1));
     const int* const lvo = w.lvoff + ((jn & 1) << 5);
+    const int kbase = ((jn + 1) / R) * R;
     for (int task = tid; task < 2 * half; task += nt) {
       const int par = task >= half ? 1 : 0;          // warp-uniform: the two parities are separate code paths
-      int key = task - par * half;
-      if (key >= R) continue;
+      const int slot = task - par * half;
+      if (slot >= R) continue;
       if (mem_state)
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
-      if (key < jn + 1) key += R;
-      const int i = key - jn;
+      const int i = fast_slot_key(slot, kbase, jn, R) - jn;
       if (i >= 1 && i <= nr) {
         int sm = jn - i - 6;
         if (sm > kMaxLoop) sm = kMaxLoop;
@@ -1019,14 +1026,14 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     double* const gen0 = w.vecp(kOGen0 + (ln & 1));
     double* const gen1 = w.vecp(kOGen1 + (ln & 1));
     const int* const lvo = w.lvoff + ((ln & 1) << 5);
+    const int kbase = ((ln + 1) / R) * R;
     for (int task = tid; task < 2 * half; task += nt) {
       const int par = task >= half ? 1 : 0;
-      int key = task - par * half;
-      if (key >= R) continue;
+      const int slot = task - par * half;
+      if (slot >= R) continue;
       if (mem_state)
         for (int q = 0; q < kFastLevels; q++) d[q] = w.dstate[(size_t)task * kFastLevels + q];
-      if (key < ln + 1) key += R;
-      const int k = key - ln;
+      const int k = fast_slot_key(slot, kbase, ln, R) - ln;
       if (k >= 1 && k <= nr && k <= row_max) {
         int sm = (k - 2) + (n - ln - 1);            // u1 <= k-2, u2 <= n-ln-1
         if (sm > kMaxLoop) sm = kMaxLoop;
