@@ -150,3 +150,31 @@ def test_bp_terms_match_the_oracle(emu, oracle, fast):
     o = oracle.mc_run(pr.as_oracle_dict(), 3, 1, 12, trace_interval=1)
     assert e["final_seq"] == o["final_seq"] and e["outcomes"] == o["outcomes"]
     _check_trace((e["trace_values"], e["trace_seqs"]), (o["trace_values"], o["trace_seqs"]), pr.n_term_values)
+
+
+def test_holo_fills_derived_from_the_apo_twin(emu, oracle):
+    """The fast path derives a ligand-bound ensemble from its apo fill, Z_holo = Z_apo (1 + (boltz - 1) P(plain hairpin at the
+    motif site)) with the site probability from an outside pass over the cells enclosing the site (fold_jobs.cuh, PfJob::site_ratio);
+    the oracle folds the holo ensemble directly.  One site (the shortcut), no site (ratio 1), two sites (falls back to a real fill),
+    contexts, and the float-rounded reference mode."""
+    pr = cases.rhf6_problem()
+    designs = cases.templated_designs(4, 4, n=102)
+    s1, t1 = emu.score(pr, designs, want_terms=True, fast=True)
+    s0, t0 = oracle.score_batch(pr.as_oracle_dict(), designs)
+    np.testing.assert_allclose(s1, s0, rtol=1e-12)
+    np.testing.assert_allclose(t1, t0, rtol=1e-12)
+    m = cases.THEO[0]
+    twice = "GGGAAA" + m + "AAAA" + m + "UUUCCC"
+    cst = "(" + "." * (len(twice) - 2) + ")"
+    pr2 = Problem(twice, {"m": cst}, [("m", "apo", False, 1.0), ("m", "holo", True, 1.0)], motif=cases.THEO)
+    assert emu.score(pr2, [twice], fast=True)[0] == pytest.approx(oracle.score(pr2.as_oracle_dict(), twice), rel=1e-12)
+    none = "GGGAAACCCUUUGGGAAACCCAAAGGGUUUCCC"
+    pr3 = Problem(none, {"m": "(" + "." * (len(none) - 2) + ")"}, [("m", "apo", False, 1.0), ("m", "holo", True, 1.0)], motif=cases.THEO)
+    assert emu.score(pr3, [none], fast=True)[0] == pytest.approx(oracle.score(pr3.as_oracle_dict(), none), rel=1e-12)
+    prc = cases.rhf6_problem(contexts=cases.SPACERS[:3])
+    np.testing.assert_allclose(emu.score(prc, designs[:2], fast=True), oracle.score_batch(prc.as_oracle_dict(), designs[:2])[0], rtol=1e-12)
+    prf = cases.rhf6_problem(float_dg=True)
+    np.testing.assert_allclose(emu.score(prf, designs[:2], fast=True), oracle.score_batch(prf.as_oracle_dict(), designs[:2], float_dg=True)[0], rtol=1e-4)
+    # only holo terms: the apo twin is added behind the scenes
+    prh = Problem(pr.seq, pr.macrostates, [("active", "holo", True, 1.0)], motif=cases.THEO)
+    np.testing.assert_allclose(emu.score(prh, designs[:2], fast=True), oracle.score_batch(prh.as_oracle_dict(), designs[:2])[0], rtol=1e-12)
