@@ -14,6 +14,7 @@
 #include "../../include/addapt_b200.h"
 #include "constraints.h"
 #include "design_core.cuh"
+#include "energy_model.h"
 
 namespace adp {
 
@@ -55,6 +56,28 @@ inline void compile_problem(const adp_problem& pr, double kT_kcal, CompiledProbl
     const int nx = sp.nb[x] + sp.n + sp.na[x];
     if (nx > ADP_MAX_LEN) throw std::string("device + context longer than the engine's maximum length");
     if (nx > sp.n_max) sp.n_max = nx;
+  }
+  // An enforced pair between two FIXED nucleotides that cannot pair canonically: ViennaRNA keeps such a pair as "pair type 7"
+  // (vrna_hc_add_bp resets the type of an enforced non-canonical pair), these kernels would give it weight 0 (P = 0, log P = -inf).
+  // That divergence is refused loudly rather than returned silently; mutable pairs are kept complementary by the moves.
+  for (int m = 0; m < pr.n_macro; m++) {
+    if (!pr.macro_cst || !pr.macro_cst[m] || (int)std::strlen(pr.macro_cst[m]) != pr.n) continue;      // reported below
+    std::vector<int> open;
+    for (int p = 0; p < pr.n; p++) {
+      const char ch = pr.macro_cst[m][p];
+      if (ch == '(') open.push_back(p);
+      else if (ch == ')' && !open.empty()) {
+        const int q = open.back();
+        open.pop_back();
+        const char a = pr.init_seq[q], b = pr.init_seq[p];
+        if (std::islower((unsigned char)a) && std::islower((unsigned char)b)) {
+          const int ta = EnergyModel::encode(a), tb = EnergyModel::encode(b);
+          if (ta && tb && !EnergyModel::pair_type(ta, tb))
+            throw std::string("macrostate ") + std::to_string(m) + " enforces the non-canonical pair " + a + std::to_string(q) + "-" + b + std::to_string(p) +
+                " between fixed positions: ViennaRNA folds it as pair type 7, this engine does not support that";
+        }
+      }
+    }
   }
   out->csts.resize((size_t)sp.n_ctx * (sp.n_macro > 0 ? sp.n_macro : 1));
   for (int x = 0; x < sp.n_ctx; x++)

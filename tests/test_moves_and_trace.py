@@ -178,3 +178,14 @@ def test_holo_fills_derived_from_the_apo_twin(emu, oracle):
     # only holo terms: the apo twin is added behind the scenes
     prh = Problem(pr.seq, pr.macrostates, [("active", "holo", True, 1.0)], motif=cases.THEO)
     np.testing.assert_allclose(emu.score(prh, designs[:2], fast=True), oracle.score_batch(prh.as_oracle_dict(), designs[:2])[0], rtol=1e-12)
+
+
+def test_enforced_non_canonical_fixed_pair_is_refused(emu):
+    """ViennaRNA keeps an enforced non-canonical pair as pair type 7; the kernels here would silently give it weight 0.  A design
+    problem whose macrostate enforces such a pair between two fixed positions is refused with an error instead."""
+    seq = "gggaaaCCCaaaUUUaga"            # g0 .. a17 enforced: G-A
+    cst = "(" + "." * (len(seq) - 2) + ")"
+    with pytest.raises(ValueError, match="non-canonical"):
+        emu.score(Problem(seq, {"m": cst}, [("m", "apo", True, 1.0)]), [seq.upper()])
+    ok = "gggaaaCCCaaaUUUagc"             # G-C: fine
+    emu.score(Problem(ok, {"m": cst}, [("m", "apo", True, 1.0)]), [ok.upper()])
