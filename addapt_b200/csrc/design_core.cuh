@@ -201,11 +201,7 @@ ADP_HD double score_construct(const E& ex, const ScoreProblemDev& sp, const uint
         job.dens = d.bp_out + kMaxBp;
       }
       if constexpr (kFast) {
-        #if defined(ADP_DESIGN_TWO_INST)
-        if (!run_pf_job_fast<E, false>(ex, job, fold_small, mats, dstate, qm_ext)) {
-#else
         if (!run_pf_job_fast<E, true>(ex, job, fold_small, mats, dstate, qm_ext)) {
-#endif
           if (declined) *declined = true;
           return 0.;
         }

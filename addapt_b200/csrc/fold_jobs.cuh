@@ -108,11 +108,7 @@ ADP_HD void run_pf_job(const E& ex, const PfJob& job, void* small, double* mats)
 // span the sequence and every pair is allowed).  The score / Monte-Carlo kernels alternate constrained and unconstrained fills;
 // with one instantiation they keep ONE copy of the sweep (~30 KB of SASS) hot instead of two against a 32 KB instruction cache
 // (ncu, round 2: stall_no_instruction 3.4 -> see profiles/r2_design_icache.md).
-#if defined(ADP_ALWAYS_CST)
-template <class E, bool kOneCstPath = true>
-#else
 template <class E, bool kOneCstPath = false>
-#endif
 ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* mats, double* dstate = nullptr, double* qm_ext = nullptr) {
   const int n = job.n;
 #if defined(ADP_PHASE_PROFILE) && defined(__CUDA_ARCH__)

@@ -391,7 +391,7 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
       const int Gs = 1 << lg, slots = nt >> lg, sub = tid & (Gs - 1);
       const int32_t* x1n_rd = w.vecp(4 + (j & 1));     // column j-2
       const int upl_j1 = kCst ? (int)c.upl[j - 1] : 1000;
-      const int sj = c.S[j], sj1 = c.S[j - 1], cpj = cp[j];
+      const int sj = c.S[j], cpj = cp[j];
       for (int slot0 = 0; slot0 < m; slot0 += slots) {
         const int slot = slot0 + (tid >> lg);
         const bool valid = slot < m;
@@ -399,7 +399,7 @@ ADP_HD int mfe_fast_fill(const E& ex, const SeqCtx& c, const MfeHot& H, const In
         int best = kInf;
         int type = 0;
         if (valid) {
-          const int si = c.S[i], si1 = c.S[i + 1];
+          const int si = c.S[i];
           type = pair_type(si, sj);
           const int codeij = (cn[i] << 4) | cpj;
           const int room = j - i - 6;

@@ -532,11 +532,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
         if (sm > kMaxLoop) sm = kMaxLoop;
         sm -= par;                                     // level Q is on iff 4 + 2Q <= sm
         double gen = 0.;
-#if defined(ADP_X_NOLEVELS)
-        if (false) {
-#else
         if (sm + par >= 4) {
-#endif
           int sm1 = sm, sm2 = sm;
           if (kCst) {
             const int upr_i1 = (int)c.upr[i + 1];
@@ -581,11 +577,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       iscell[i] = type != 0;
       if (type != 0) {
         cells[ex.atomic_inc(counter)] = (uint16_t)i;
-#if defined(ADP_X_NOHP)
-        hp[i] = 0.01;
-#else
         hp[i] = fast_hairpin<kCst>(c, H, G, w, motif_boltz, i, jn, type);
-#endif
       }
     }
   };
@@ -708,11 +700,9 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
       const int l = j + 3 - S;
       w.lvoff[((j & 1) << 5) + t] = (((l - 4) * (l - 5)) >> 1) * (int)sizeof(double);
     }
-#if !defined(ADP_LEVELS_LAST)
     // level sums first: every warp runs the same code at the same time (instruction-cache locality), then the warps split
     // into those that hold cells and those that do the rest of the phase
     if (j < n) levels(j + 1);
-#endif
     // ---- cells(j): Qb(i,j) for the listed cells, a lane group per cell
     if (m > 0) {
       const double* const hp = w.vecp(kVHp + (j & 1));
@@ -747,7 +737,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
           if (room >= 0) {
             // corner candidates through the code-indexed table, one per lane and round.  Software-pipelined and kept rolled (code
             // size): the table load of a round is issued in that round and consumed in the next, the last one after the filters below.
-#if !defined(ADP_X_NOCORNER)
             if (sub == Gs - 1) {
               // the stack (u1 = u2 = 0) as straight-line code on the group's last lane: both types come from the cell's own codes
               const double v = qb[t4(i + 1, j - 1)] * H.RI[(cn[j - 1] << 4) | cp[i + 1]];
@@ -774,9 +763,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               cval = v2;
               ctab = t2;
             }
-#endif
             ADP_TICK(9)
-#if !defined(ADP_X_NOAXIS)
             // The four 1-D filters along the loop's axes, fused into one loop so that their load chains overlap:
             //   bulges with the unpaired run on the 3' side (k = i+1, l = j-1-u, u >= 2) and on the 5' side (l = j-1, k = i+1+u:
             //   premultiplied column vector xA);  1 x u loops (k = i+2, l = j-1-u, u >= 3) and u x 1 loops (l = j-2, k = i+1+u:
@@ -803,11 +790,9 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
                 acc1n += H.tap1n[u] * ((u <= hi13 ? n3 : 0.) + (u <= hi31 ? n5 : 0.));
               }
             }
-#endif
           }
           ADP_TICK(10)
           // multiloop closed by (i,j): Qm(i+1,k-1) * Qm1(k,j-1), k = i+6 .. j-5
-#if !defined(ADP_X_NOML)
           {
             int k = i + 6 + sub;
             int off = t4(i + 1, k - 1);
@@ -821,7 +806,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
               pq += Gs;
             }
           }
-#endif
           // ---- cell total
           other += cval * ctab;
           acc = other + au_factor(H, si, sj) * accB + H.R1[codeij] * H.FI[codeij] * acc1n + accML * (H.MLclosing * (H.RM[codeij] * H.FI[codeij]) * H.scale2);
@@ -842,9 +826,6 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     }
     ADP_TICK(0)
     // ---- everything else of the phase
-#if defined(ADP_LEVELS_LAST)
-    if (j < n) levels(j + 1);
-#endif
     ADP_TICK(4)
     if (j < n) list_rows(j + 1);
     if (j >= 5 && j <= n) rest_rows(j);
@@ -852,9 +833,7 @@ ADP_HD double fast_inside(const E& ex, const SeqCtx& c, const PfHot& H, const Pf
     if (j >= 6 && ex.warp() == nwarp - 1) q1_task(j - 1);
     if (j >= 6 && j <= n && ex.warp() == (nwarp > 1 ? nwarp - 2 : 0)) scan_unpaired(j - 1);
     ADP_TICK(3)
-#if !defined(ADP_X_NOQM)
     if (j >= 7) drain_qm(j - 2);
-#endif
     ADP_TICK(6)
     ex.sync();
     ADP_TICK(7)
@@ -916,7 +895,6 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
                          FastWork& w, const FastOut& out) {
   const int n = c.n, nt = ex.nthreads(), tid = ex.tid(), ld = w.ld, R = w.R;
   const int nt_lg = ilog2_floor((unsigned)nt), warp_lg = ilog2_floor((unsigned)E::kWarp);
-  const int nwarp = nt >> warp_lg;
   const bool mem_state = E::kSerial || w.dstate != nullptr;   // level sums in memory: host emulation, or more anti-diagonals than threads
   const int half = mem_state ? R : (nt >> 1);        // anti-diagonal slots per level parity (>= R)
   double* const qb = w.qb;
@@ -982,9 +960,6 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
   // multiloop carrier A(., ln) for every possible 5' closing position i <= ln-5: rows from a queue, a warp-sized chunk at a time
   auto carriers = [&](int ln) {
     const int nrow = ln - 5 < row_max - 1 ? ln - 5 : row_max - 1;      // rows a listed cell can read: i < k <= row_max
-#if defined(ADP_X_OUT_NOCARRIER)
-    if (true) return;
-#endif
     if (ln >= n || nrow < 1) return;
     double* const vA = w.vecp(kOA + (ln & 1));
     const int lg = E::kSerial ? 0 : group_lg(nrow, nt_lg, warp_lg);      // rows fill the CTA once (1, 2, 4 and 8 lanes per row measured: all slower)
@@ -1039,11 +1014,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
         if (sm > kMaxLoop) sm = kMaxLoop;
         sm -= par;                                  // level Q is on iff 4 + 2Q <= sm
         double gen = 0.;
-#if defined(ADP_X_OUT_NOLEVELS)
-        if (false) {
-#else
         if (k >= 4 && ln + 3 <= n && sm + par >= 4) {
-#endif
           const int room1 = n + 1 - ln - par;        // row candidate needs j = ln+S-1 <= n
           const int room2 = k - par;                 // column candidate needs i = k+1-S >= 1
           int sm1 = sm < room1 ? sm : room1, sm2 = sm < room2 ? sm : room2;
@@ -1156,9 +1127,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
       w.lvoff[((l & 1) << 5) + t] = (((j - 4) * (j - 5)) >> 1) * (int)sizeof(double);
     }
     const bool more = l > kTurn + 2 && l > l_min;      // another column follows
-#if !defined(ADP_LEVELS_LAST)
     if (more) levels(l - 1);      // first, by every warp at the same time (see the inside pass)
-#endif
     // ---- cells(l): outside weight of every listed pair (k,l)
     if (m > 0) {
       const double* const gen0 = w.vecp(kOGen0 + (l & 1));
@@ -1202,7 +1171,6 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
           ADP_TICK(8)
           if (k >= 2 && l < n) {
             const int t2r = rtype(type);
-#if !defined(ADP_X_OUT_NOCORNER)
             if (sub == Gs - 1) {
               // the enclosing stack (i,j) = (k-1,l+1) as straight-line code on the group's last lane
               const double v = qb[t4(k - 1, l + 1)] * H.RI[(cn[k - 1] << 4) | cp[l + 1]];
@@ -1228,9 +1196,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
               cval = v2;
               ctab = t2;
             }
-#endif
             ADP_TICK(9)
-#if !defined(ADP_X_OUT_NOAXIS)
             // the four 1-D filters fused into one loop like in the inside pass: enclosing bulges (i = k-1, j = l+1+u / j = l+1,
             // i = k-1-u: column vector xA), enclosing 1 x u loops (i = k-2, j = l+1+u, u >= 3) and u x 1 loops (j = l+2,
             // i = k-1-u: column vector x1n).
@@ -1255,9 +1221,7 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
                 acc1n += H.tap1n[u] * (n3 + (u <= hi31 ? n5 : 0.));
               }
             }
-#endif
             ADP_TICK(10)
-#if !defined(ADP_X_OUT_NOML)
             // (k,l) is a stem of a multiloop closed by (i,j), i < k, j > l:  u = k-1-i unpaired bases left of k
             {
               const double* qcol = qm + t4(1, k - 1) - 1;       // Qm(i+1,k-1) = qcol[i+1], valid for i+1 <= k-5
@@ -1269,7 +1233,6 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
                 accML += t;
               }
             }
-#endif
           }
           // ---- cell total
           other += cval * ctab;
@@ -1299,9 +1262,6 @@ ADP_HD void fast_outside(const E& ex, const SeqCtx& c, const PfHot& H, const PfT
     }
     ADP_TICK(0)
     // ---- everything else of the phase
-#if defined(ADP_LEVELS_LAST)
-    if (more) levels(l - 1);
-#endif
     ADP_TICK(4)
     if (more) list_rows(l - 1);
     if (l <= n && l > kTurn + 1) rest_rows(l);
