@@ -3,16 +3,16 @@
 L0 ~6 KB, L1.5 32 KB per SM -- so the hot loop bodies are kept compact).   python tools/code_size.py [lib.so]"""
 import collections, os, re, subprocess, sys, tempfile
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-KERNEL = "mfe" if "--kernel=mfe" in sys.argv else "pf"
+KERNEL = "mfe" if "--kernel=mfe" in sys.argv else "mc" if "--kernel=mc" in sys.argv else "pf"      # mc: the PF sweep inside mc_kernel<true,1,true,false>
 lib = args[0] if args else "addapt_b200/libaddapt_b200.so"
-src_path = "addapt_b200/csrc/%s_fast.cuh" % KERNEL
+src_path = "addapt_b200/csrc/%s_fast.cuh" % ("mfe" if KERNEL == "mfe" else "pf")
 src_name = os.path.basename(src_path)
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "fold_kernels", os.path.abspath(lib)], cwd=tmp, capture_output=True)
+subprocess.run(["cuobjdump", "-xelf", "design_kernels" if KERNEL == "mc" else "fold_kernels", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 sass = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
 sec = [i for i, l in enumerate(sass) if re.match(r"\s*\.section\s*\.text\.", l)]
-a = [i for i in sec if ("pf_fast_kernelILi256ELb1ELb0" if KERNEL == "pf" else "mfe_fast_kernelILi256ELb1") in sass[i]][0]
+a = [i for i in sec if {"pf": "pf_fast_kernelILi256ELb1ELb0", "mfe": "mfe_fast_kernelILi256ELb1", "mc": "mc_kernelILb1ELi1ELb1ELb0"}[KERNEL] in sass[i]][0]
 b = min(i for i in sec + [len(sass)] if i > a)
 instrs, chain, pend = [], [], []
 for ln in sass[a:b]:
@@ -30,7 +30,7 @@ def find(sub, start=0):
         if sub in src[i]:
             return i + 1
     return None
-if KERNEL == "pf":
+if KERNEL != "mfe":
     ins_a, out_a = find("ADP_HD double fast_inside("), find("ADP_HD void fast_outside(")
 else:
     ins_a, out_a = find("ADP_HD int mfe_fast_fill("), len(src) + 1
@@ -48,7 +48,7 @@ MM = [("ADP_HD int mfe_fast_fill(", "fill.init"), ("auto prepare_column", "fill.
       ("// j = 4 is a warm-up", "fill.colhead"), ("// ---- interval 1: C(i,j)", "fill.cells.head"), ("// corner candidates, software-pipelined", "fill.cells.corners"),
       ("// the four 1-D filters along", "fill.cells.axis"), ("int k = i + 6 + sub;", "fill.cells.ml"), ("other = imin(other, cadd + ctab);", "fill.cells.fin"),
       ("// ---- interval 2: shifted copies", "fill.int2")]
-if KERNEL == "pf":
+if KERNEL != "mfe":
     marks = sorted([(find(s, ins_a), n) for s, n in MI if find(s, ins_a)] + [(find(s, out_a), n) for s, n in MO if find(s, out_a)])
 else:
     marks = sorted([(find(s, ins_a), n) for s, n in MM if find(s, ins_a)])
