@@ -68,3 +68,54 @@ def write_tsv(path, problem, values, seqs, num_steps, context_names=None):
         f.write("\t".join(header(problem, context_names)) + "\t\n")
         for r in rows(problem, values, seqs, num_steps, context_names):
             f.write("\t".join(r) + "\t\n")
+
+
+# ---- reading trajectory files back: what the reference's tools/utils.py does with them (pandas-free) -----------------------------
+
+def load_initial_seq(tsv_path):
+    """the '# initial_seq <seq>' line a trajectory file starts with (reference tools/utils.py:12-25)"""
+    with open(tsv_path) as f:
+        header = f.readline()
+    if header.startswith("#"):
+        _, label, value = header.rstrip("\n").split("\t")[:3]
+        if label == "initial_seq":
+            return value
+    return None
+
+
+def load_trajectory(tsv_path):
+    """column name -> list of values (floats where the text parses as one), comment lines skipped (reference tools/utils.py:6-7:
+    pandas.read_table(path, comment='#'))"""
+    cols, data = None, None
+    with open(tsv_path) as f:
+        for line in f:
+            if line.startswith("#") or not line.strip():
+                continue
+            cells = line.rstrip("\n").split("\t")
+            if cells and cells[-1] == "":
+                cells = cells[:-1]                       # every line of the format ends with a tab
+            if cols is None:
+                cols, data = cells, [[] for _ in cells]
+                continue
+            for k, c in enumerate(cells[:len(cols)]):
+                try:
+                    data[k].append(float(c))
+                except ValueError:
+                    data[k].append(c)
+    return dict(zip(cols or [], data or []))
+
+
+def pick_best_seqs(tsv_paths, window_size):
+    """The designs the reference's offline tools would pick from a set of trajectory files (reference tools/utils.py:27-67):
+    per file, the peaks of the current_score column (sharding.pick_best_scores: arg-max, blank +-window, while >= 75th percentile),
+    each returned as (path, record index, step, score, sequence).  The snapshot's files carry the whole sequence in current_seq
+    (the reference's extract_pick still concatenates the 'current_domain*' columns of an older format)."""
+    from .sharding import pick_best_scores
+    picks = []
+    for path in tsv_paths:
+        traj = load_trajectory(path)
+        if not traj or not traj.get("current_score"):
+            continue
+        for i in pick_best_scores(traj["current_score"], window_size):
+            picks.append((path, i, int(traj["step"][i]), traj["current_score"][i], traj["current_seq"][i]))
+    return picks

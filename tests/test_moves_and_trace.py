@@ -189,3 +189,27 @@ def test_enforced_non_canonical_fixed_pair_is_refused(emu):
         emu.score(Problem(seq, {"m": cst}, [("m", "apo", True, 1.0)]), [seq.upper()])
     ok = "gggaaaCCCaaaUUUagc"             # G-C: fine
     emu.score(Problem(ok, {"m": cst}, [("m", "apo", True, 1.0)]), [ok.upper()])
+
+
+def test_picks_from_trajectory_files(emu, tmp_path):
+    """the pick / merge half of SURVEY.md 8(f1): trajectory files of several runs -> the designs the reference's tools would
+    select (tools/utils.py:27-51), read back without pandas"""
+    pr = small_problem()
+    paths = []
+    for t in range(3):
+        r = emu.mc_run(pr, 5, t, 40, trace_interval=1)
+        p = str(tmp_path / ("traj.%d.tsv" % t))
+        trajectory.write_tsv(p, pr, r["trace_values"], r["trace_seqs"], 40)
+        paths.append(p)
+        traj = trajectory.load_trajectory(p)
+        assert trajectory.load_initial_seq(p) == pr.seq
+        assert traj["step"] == [float(s) for s in range(40)] and traj["current_seq"][-1] == r["final_seq"]
+        np.testing.assert_allclose(traj["current_score"], r["trace_values"][:, 1], rtol=1e-5)
+        assert set(traj["outcome"]) <= set(trajectory.OUTCOMES)
+    picks = trajectory.pick_best_seqs(paths, 3)
+    assert picks and {p[0] for p in picks} <= set(paths)
+    for path, i, step, score, seq in picks:
+        traj = trajectory.load_trajectory(path)
+        assert step == i and seq == traj["current_seq"][i] and score == traj["current_score"][i]
+        assert score >= np.percentile(traj["current_score"], 75) - 1e-12       # a peak is at least at the 75th percentile
+        assert len(seq) == len(pr.seq)
