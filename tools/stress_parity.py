@@ -21,8 +21,8 @@ t0 = time.time()
 n_fold = n_seq = 0
 worst_dg = worst_bp = 0.0
 while time.time() - t0 < budget:
-    n = int(rng.integers(5, 200))
-    B = int(rng.integers(8, 64))
+    n = int(rng.integers(5, 200)) if rng.random() < 0.97 else int(rng.integers(200, 321))      # a few long constructs (up to ADP_MAX_LEN)
+    B = int(rng.integers(8, 64)) if n < 200 else int(rng.integers(4, 17))
     alphabet = ["ACGU", "GC", "GU", "ACGU", "AU", "ACGU"][int(rng.integers(0, 6))]
     seqs = ["".join(alphabet[k] for k in rng.integers(0, len(alphabet), n)) for _ in range(B)]
     motif = cases.THEO if rng.random() < 0.5 else None
@@ -46,5 +46,5 @@ while time.time() - t0 < budget:
     assert np.array_equal(e1, e0) and s1 == s0, ("mfe mismatch", n, cst, motif is not None)
     n_fold += 1
     n_seq += B
-print("stress parity ok: %d batches, %d sequences, lengths 5-199; worst dG rel err %.2e, worst bppm excess err %.2e" % (n_fold, n_seq, worst_dg, worst_bp))
+print("stress parity ok: %d batches, %d sequences, lengths 5-320; worst dG rel err %.2e, worst bppm excess err %.2e" % (n_fold, n_seq, worst_dg, worst_bp))
 eng.close()
