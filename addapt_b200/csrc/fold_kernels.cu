@@ -123,12 +123,18 @@ __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) pf_fast_ker
   }
   // constructs longer than threads/2 have more anti-diagonals than threads: their level sums live in global scratch too
   double* dstate = n > fast_max_len(kThreads) ? slab + gused : nullptr;
-  for (int jid = blockIdx.x; jid < jobs; jid += gridDim.x) {
-    const PfJob job = make_pf_job(a, jid);
-    const bool done = run_pf_job_fast(ex, job, small, mats, dstate, qm_ext);
-    if (!done && threadIdx.x == 0) { a.redo[jid] = 1; atomicAdd(a.redo + jobs, 1); }
-    __syncthreads();   // the next job reuses the working set
-  }
+  // Large batches are walked design-major: a CTA folds all variants of a sequence (apo, holo) back to back, so the second
+  // variant finds the sequence's corner-table entries in L1.  Small batches stay job-major (every job on its own CTA).
+  const bool by_design = a.B >= (int)gridDim.x;
+  const int units = by_design ? a.B : jobs, per = by_design ? a.V : 1;
+  for (int u = blockIdx.x; u < units; u += gridDim.x)
+    for (int v = 0; v < per; v++) {
+      const int jid = u * per + v;
+      const PfJob job = make_pf_job(a, jid);
+      const bool done = run_pf_job_fast(ex, job, small, mats, dstate, qm_ext);
+      if (!done && threadIdx.x == 0) { a.redo[jid] = 1; atomicAdd(a.redo + jobs, 1); }
+      __syncthreads();   // the next job reuses the working set
+    }
 }
 
 // Fast MFE path (mfe_fast.cuh): int32 matrices are half the size of the PF ones, so up to four constructs share an SM.
