@@ -164,3 +164,13 @@ def test_gather_top_designs_on_the_device(engine):
     b = gather_top_designs_device(engine, torch.from_numpy(scores).cuda(), torch.from_numpy(seqs).cuda(), 500, k)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_golden_trajectory_file_on_the_device(engine, tmp_path):
+    """the frozen oracle trajectory (tests/golden/oracle_trajectory.tsv) reproduced by the Monte-Carlo kernel"""
+    from tests.test_moves_and_trace import GOLDEN_TSV, _same_tsv
+    pr = small_problem()
+    r = engine.mc_run(pr, 1, 2016, 30, traj_id0=7, trace_interval=1)
+    path = str(tmp_path / "gpu.tsv")
+    trajectory.write_tsv(path, pr, r["trace_values"][0], r["trace_seqs"][0], 30)
+    _same_tsv(path, GOLDEN_TSV)

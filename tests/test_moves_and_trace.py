@@ -213,3 +213,51 @@ def test_picks_from_trajectory_files(emu, tmp_path):
         assert step == i and seq == traj["current_seq"][i] and score == traj["current_score"][i]
         assert score >= np.percentile(traj["current_score"], 75) - 1e-12       # a peak is at least at the 75th percentile
         assert len(seq) == len(pr.seq)
+
+
+def _same_tsv(path_a, path_b):
+    la, lb = open(path_a).read().split("\n"), open(path_b).read().split("\n")
+    assert la[:2] == lb[:2] and len(la) == len(lb)
+    for x, y in zip(la[2:], lb[2:]):
+        cx, cy = x.split("\t"), y.split("\t")
+        assert len(cx) == len(cy)
+        for u, v in zip(cx, cy):
+            if u != v:                                    # numbers printed with 6 digits may differ in the last one
+                assert float(u) == pytest.approx(float(v), rel=2e-5, abs=1e-9), (x, y)
+
+
+GOLDEN_TSV = os.path.join(GOLD, "oracle_trajectory.tsv")
+
+
+def test_golden_trajectory_file(emu, oracle, tmp_path):
+    """tests/golden/oracle_trajectory.tsv (tests/golden/make_trajectory_golden.py): the reference's on-disk format, the
+    random-stream convention and the scores, frozen; a fresh oracle run and the emulation of the kernel source reproduce it"""
+    pr = small_problem()
+    head = open(GOLDEN_TSV).read().split("\n")[:2]
+    assert head[0] == "#\tinitial_seq\t" + pr.seq
+    assert head[1] == ("step\tnum_steps\tcurrent_score\tproposed_score\tterm_weight[apo: not act]\tterm_value[apo: not act]\tterm_weight[holo: act]\t"
+                       "term_value[holo: act]\tscore_diff\ttemperature\tmetropolis_criterion\trandom_threshold\tmove\toutcome\tcurrent_seq\tproposed_seq\t")
+    o = oracle.mc_run(pr.as_oracle_dict(), 2016, 7, 30, trace_interval=1)
+    a = str(tmp_path / "oracle.tsv")
+    trajectory.write_tsv(a, pr, o["trace_values"], o["trace_seqs"], 30)
+    _same_tsv(a, GOLDEN_TSV)
+    for fast in (False, True):
+        e = emu.mc_run(pr, 2016, 7, 30, fast=fast, trace_interval=1)
+        b = str(tmp_path / ("emu%d.tsv" % fast))
+        trajectory.write_tsv(b, pr, e["trace_values"], e["trace_seqs"], 30)
+        _same_tsv(b, GOLDEN_TSV)
+
+
+def test_nccl_log_helpers(tmp_path, monkeypatch, capsys):
+    from addapt_b200 import sharding
+    for var in ("NCCL_DEBUG", "NCCL_DEBUG_SUBSYS", "NCCL_DEBUG_FILE"):
+        monkeypatch.delenv(var, raising=False)
+    assert sharding.nccl_log_begin(1) is None and "NCCL_DEBUG" not in os.environ            # one rank: nothing to log
+    monkeypatch.setenv("NCCL_DEBUG", "VERSION")                                              # quieter than INFO: raised
+    path = sharding.nccl_log_begin(2)
+    assert os.environ["NCCL_DEBUG"] == "INFO" and os.environ["NCCL_DEBUG_SUBSYS"] == "INIT" and os.environ["NCCL_DEBUG_FILE"] == path
+    open(path, "w").write("host:1:1 [0] NCCL INFO comm 0x1 rank 0 nranks 2\n")
+    sharding.nccl_log_end(path)
+    assert "nranks 2" in capsys.readouterr().err and not os.path.exists(path)
+    monkeypatch.setenv("NCCL_DEBUG_FILE", "/somewhere/else")                                 # the caller's own file is respected
+    assert sharding.nccl_log_begin(2) is None and os.environ["NCCL_DEBUG_FILE"] == "/somewhere/else"
