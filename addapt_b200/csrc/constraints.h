@@ -41,6 +41,11 @@ inline void build_constraint(const std::string& cst, int n, ConstraintDev* out) 
     }
   }
   if (depth) throw std::string("unbalanced brackets in constraint");
+  // run lengths of positions that may stay unpaired ('.' and 'x'): upr counts p, p+1, ..., upl counts p, p-1, ...
+  out->upr[n + 1] = out->upr[n + 2] = 0;
+  for (int p = n; p >= 1; p--) out->upr[p] = (out->flag[p] & 2) ? 0 : (uint16_t)(out->upr[p + 1] + 1);
+  out->upr[0] = out->upl[0] = out->upl[n + 1] = 0;
+  for (int p = 1; p <= n; p++) out->upl[p] = (out->flag[p] & 2) ? 0 : (uint16_t)(out->upl[p - 1] + 1);
 }
 
 }  // namespace adp

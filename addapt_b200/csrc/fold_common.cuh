@@ -129,6 +129,8 @@ struct ConstraintDev {
   uint16_t partner[kMaxLen + 2];
   uint16_t enc[kMaxLen + 2];
   uint8_t flag[kMaxLen + 2];
+  uint16_t upr[kMaxLen + 3];   // run lengths of positions that may stay unpaired (see SeqCtx::upr / upl); a function of the
+  uint16_t upl[kMaxLen + 2];   // constraint alone, so build_constraint computes them once instead of every fill
 };
 
 constexpr int kMaxVariants = 8;
@@ -192,27 +194,23 @@ ADP_HD bool can_unpair(const SeqCtx& c, int p) { return !c.has_cst || !(c.flag[p
 template <class E>
 ADP_HD void load_context(const E& ex, SeqCtx& c, const uint8_t* seq, const ConstraintDev* cst, const MotifDev* motif) {
   const int n = c.n;
-  for (int p = ex.tid(); p <= n + 1; p += ex.nthreads()) {
-    c.S[p] = (p >= 1 && p <= n) ? (uint8_t)encode_nt(seq[p - 1]) : 0;
-    if (cst) {
-      c.flag[p] = (p >= 1 && p <= n) ? cst->flag[p] : 0;
-      c.partner[p] = (p >= 1 && p <= n) ? cst->partner[p] : 0;
-      c.enc[p] = (p >= 1 && p <= n) ? cst->enc[p] : 0;
-    } else {
-      c.flag[p] = 0; c.partner[p] = 0; c.enc[p] = 0;
+  for (int p = ex.tid(); p <= n + 2; p += ex.nthreads()) {
+    const bool in = p >= 1 && p <= n;
+    if (p <= n + 1) {
+      c.S[p] = in ? (uint8_t)encode_nt(seq[p - 1]) : 0;
+      if (cst) {
+        c.flag[p] = in ? cst->flag[p] : 0;
+        c.partner[p] = in ? cst->partner[p] : 0;
+        c.enc[p] = in ? cst->enc[p] : 0;
+      } else {
+        c.flag[p] = 0; c.partner[p] = 0; c.enc[p] = 0;
+      }
+      c.motif_at[p] = 0;
+      c.upl[p] = in ? (cst ? cst->upl[p] : (uint16_t)p) : 0;
     }
-    c.motif_at[p] = 0;
+    c.upr[p] = in ? (cst ? cst->upr[p] : (uint16_t)(n - p + 1)) : 0;     // run lengths: see ConstraintDev
   }
   ex.sync();
-  if (ex.tid() == 0) {     // run lengths: one short serial pass (n <= 320)
-    c.upr[n + 1] = 0;
-    c.upr[n + 2] = 0;
-    for (int p = n; p >= 1; p--) c.upr[p] = can_unpair(c, p) ? (uint16_t)(c.upr[p + 1] + 1) : 0;
-    c.upr[0] = 0;
-    c.upl[0] = 0;
-    for (int p = 1; p <= n; p++) c.upl[p] = can_unpair(c, p) ? (uint16_t)(c.upl[p - 1] + 1) : 0;
-    c.upl[n + 1] = 0;
-  }
   if (motif && motif->len > 0) {
     const int m = motif->len;
     for (int p = 1 + ex.tid(); p + m - 1 <= n; p += ex.nthreads()) {
