@@ -155,15 +155,12 @@ ADP_HD bool run_pf_job_fast(const E& ex, const PfJob& job, void* small, double* 
   if (job.site_ratio && job.site_motif && !job.motif) {
     // Z_holo / Z_apo from the apo matrices (see FastOut): where does the motif occur?
     const int mlen = job.site_motif->len;
-    if (ex.tid() == 0) {
-      int count = 0, at = 0;
-      for (int p = 1; p + mlen - 1 <= n; p++)
-        if (c.motif_at[p]) { count++; at = p; }
-      w.counter[0] = count;
-      w.counter[1] = at;
-      *job.site_ratio = count == 0 || !(Z > 0.) ? 1. : (double)NAN;      // no site, or an empty ensemble: nothing to reweight
-    }
+    if (ex.tid() == 0) { w.counter[0] = 0; w.counter[1] = 0; }      // every thread is past the fill's last use of the counters
     ex.sync();
+    for (int p = 1 + ex.tid(); p + mlen - 1 <= n; p += ex.nthreads())
+      if (c.motif_at[p]) { ex.atomic_inc(&w.counter[0]); w.counter[1] = p; }   // the position is used for a single site only
+    ex.sync();
+    if (ex.tid() == 0) *job.site_ratio = w.counter[0] == 0 || !(Z > 0.) ? 1. : (double)NAN;      // no site, or an empty ensemble: nothing to reweight
     if (w.counter[0] == 1 && Z > 0.) {
       const int at = w.counter[1];
       ex.sync();                      // the counters are reused by the outside pass
