@@ -338,3 +338,19 @@ def test_kernel_source_in_emulation_equals_the_explicit_sum(oracle, emu, seq, cs
 @pytest.mark.parametrize("seq,cst,motif", KERNEL_CASES)
 def test_engine_equals_the_explicit_sum(oracle, engine, seq, cst, motif):
     check(oracle, seq, cst=cst, motif=motif, fold=_Device(engine), tol=1e-9)
+
+
+@pytest.mark.parametrize("seq,cst,motif", [
+    ("GGGAAACCCAGGGAAACCC", "(.................)", None),
+    ("GGGAAACCCAGGGAAACCC", ".x......x..........", None),
+    ("GGGCGAAAAGCCCAUGGC", "..(.......).......", MOTIF),       # the ligand-binding hairpin itself
+    ("GGGCGAAAAGCCCAUGGC", "xx................", MOTIF),
+])
+def test_macrostate_probability_is_the_share_of_the_satisfying_structures(oracle, seq, cst, motif):
+    """RnaFold::macrostate_prob (reference src/scoring.cc:53-71): exp((G_all - G_constrained)/kT) = weight of the structures that
+    satisfy the constraint / weight of all structures"""
+    g_all, _, _ = enumerate_ensemble(oracle, seq, None, motif)
+    g_cst, _, _ = enumerate_ensemble(oracle, seq, cst, motif)
+    want = math.exp((g_all - g_cst) / oracle.kT)
+    assert 0. < want < 1.
+    assert oracle.macrostate_prob(seq, cst, motif=motif) == pytest.approx(want, rel=1e-9)
