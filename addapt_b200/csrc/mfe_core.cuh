@@ -165,11 +165,7 @@ ADP_HD void mfe_traceback(const E& ex, const SeqCtx& c, const IntTables& P, cons
     if (lane == 0) { w.stack[3 * sp] = (int16_t)(a); w.stack[3 * sp + 1] = (int16_t)(b); w.stack[3 * sp + 2] = (int16_t)(kind); } \
     sp++;                                                                               \
   } while (0)
-#if defined(__CUDA_ARCH__)
-#define ADP_WSYNC() __syncwarp()
-#else
-#define ADP_WSYNC() do {} while (0)
-#endif
+#define ADP_WSYNC() ex.warp_sync()
   ADP_PUSH(1, n, 0);
   const int mlb = P.ML_base;
   while (sp > 0) {

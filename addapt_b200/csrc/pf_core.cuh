@@ -162,9 +162,7 @@ ADP_HD void pf_outside(const E& ex, const SeqCtx& c, const PfSmall& P, const PfT
       e = ex.warp_sum(e);
       // all lanes keep the running value in registers would need a broadcast; lane 0 owns the array
       if (ex.lane() == 0) w.qln[k] = (can_unpair(c, k) ? w.qln[k + 1] * s1 : 0.) + e;
-#if defined(__CUDA_ARCH__)
-      __syncwarp();
-#endif
+      ex.warp_sync();
     }
   }
   ex.sync();

@@ -134,3 +134,109 @@ class Emu:
             raise self._err()
         return dict(final_seq=fs.raw[:n].decode(), final_score=fsc.value, best_seq=bs.raw[:n].decode(), best_score=bsc.value,
                     best_step=bst.value, outcomes=list(oc), trace_values=tv, trace_seqs=tq)
+
+    # ---- the emulated CTA with all of its threads (tests/emu/simt.hh, emu_simt.cc) -------------------------------------------
+    POLICIES = {"random": 0, "ascending": 1, "descending": 2, "random_warp": 3}
+
+    def _simt_err(self):
+        self.lib.emu_simt_error.restype = C.c_char_p
+        return RuntimeError("simt emulation: " + self.lib.emu_simt_error().decode())
+
+    @staticmethod
+    def _strings(items):
+        arr = (C.c_char_p * len(items))(*[_b(s) if s else None for s in items])
+        return arr
+
+    def simt_pf(self, seqs, csts=None, motif=None, use_motif=None, outside=None, path="fast", threads=256, group=1, policy="random",
+                seed=0):
+        """several partition-function jobs of one length back to back on one emulated CTA.  path: general | fast | fast_qm_ext |
+        fast_mem_levels.  -> dict(dG, bppm, declined, stats=(CTA barriers, warp collectives, context switches))"""
+        J, n = len(seqs), len(seqs[0])
+        csts = csts or [None] * J
+        use_motif = np.array(use_motif if use_motif is not None else [1 if motif else 0] * J, dtype=np.int32)
+        outside = np.array(outside if outside is not None else [1] * J, dtype=np.int32)
+        dg, bp = np.zeros(J), np.zeros((J, n * (n + 1) // 2))
+        declined, stats = np.zeros(J, dtype=np.int32), np.zeros(3, dtype=np.int64)
+        self.lib.emu_simt_pf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_char_p,
+                                         C.c_char_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+        mp = C.c_uint64()
+        rc = self.lib.emu_simt_pf(self.model, J, n, b"".join(_b(s) for s in seqs), self._strings(csts), use_motif.ctypes.data,
+                                  outside.ctypes.data, _b(motif[0]) if motif else None, _b(motif[1]) if motif else None,
+                                  motif[2] if motif else 0.0, dg.ctypes.data, bp.ctypes.data, declined.ctypes.data,
+                                  {"general": 0, "fast": 1, "fast_qm_ext": 2, "fast_mem_levels": 3}[path], threads, group,
+                                  self.POLICIES[policy], seed, stats.ctypes.data, C.byref(mp))
+        if rc:
+            raise self._simt_err()
+        # matrices: fingerprint of the matrix block as the LAST job left it (every cell, not only the outputs)
+        return dict(dG=dg, bppm=bp, declined=declined, stats=tuple(int(v) for v in stats), matrices=mp.value)
+
+    def simt_mfe(self, seqs, csts=None, motif=None, use_motif=None, path="fast", threads=256, group=1, policy="random", seed=0):
+        J, n = len(seqs), len(seqs[0])
+        csts = csts or [None] * J
+        use_motif = np.array(use_motif if use_motif is not None else [1 if motif else 0] * J, dtype=np.int32)
+        e, st = np.zeros(J, dtype=np.int32), np.zeros((J, n), dtype=np.uint8)
+        declined, stats = np.zeros(J, dtype=np.int32), np.zeros(3, dtype=np.int64)
+        self.lib.emu_simt_mfe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_char_p, C.c_char_p,
+                                          C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                          C.c_void_p, C.POINTER(C.c_uint64)]
+        mp = C.c_uint64()
+        rc = self.lib.emu_simt_mfe(self.model, J, n, b"".join(_b(s) for s in seqs), self._strings(csts), use_motif.ctypes.data,
+                                   _b(motif[0]) if motif else None, _b(motif[1]) if motif else None, motif[2] if motif else 0.0,
+                                   e.ctypes.data, st.ctypes.data, declined.ctypes.data, {"general": 0, "fast": 1, "fast_mem_levels": 3}[path],
+                                   threads, group, self.POLICIES[policy], seed, stats.ctypes.data, C.byref(mp))
+        if rc:
+            raise self._simt_err()
+        return dict(e=e, structures=[bytes(r).decode("latin-1") for r in st], declined=declined, stats=tuple(int(v) for v in stats),
+                    matrices=mp.value)
+
+    def simt_score(self, problem: Problem, seqs, fast=True, qm_global=False, threads=256, policy="random", seed=0):
+        B = len(seqs)
+        out, terms, stats = np.zeros(B), np.zeros((B, problem.n_term_values)), np.zeros(3, dtype=np.int64)
+        self.lib.emu_simt_score.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+        rc = self.lib.emu_simt_score(self.model, C.byref(problem.c), B, b"".join(_b(s) for s in seqs), out.ctypes.data, terms.ctypes.data,
+                                     1 if fast else 0, 1 if qm_global else 0, threads, self.POLICIES[policy], seed, stats.ctypes.data)
+        if rc:
+            raise self._simt_err()
+        return out, terms, tuple(int(v) for v in stats)
+
+    def simt_mc(self, problem: Problem, seed, traj_id0, n_traj, n_steps, thermostat=("annealing", 5.0, 0.0, 300), fast=True, threads=256,
+                policy="random", sched_seed=0):
+        n = problem.n
+        if thermostat[0] == "fixed":
+            kind, ta = 0, (C.c_double * 3)(thermostat[1], 0, 0)
+        elif thermostat[0] == "auto":
+            kind, ta = 2, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
+        else:
+            kind, ta = 1, (C.c_double * 3)(thermostat[1], thermostat[2], thermostat[3])
+        fs, bs = np.zeros((n_traj, n), dtype=np.uint8), np.zeros((n_traj, n), dtype=np.uint8)
+        fsc, bsc, bst = np.zeros(n_traj), np.zeros(n_traj), np.zeros(n_traj, dtype=np.int32)
+        oc, stats = np.zeros((n_traj, 4), dtype=np.uint32), np.zeros(3, dtype=np.int64)
+        self.lib.emu_simt_mc.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+        rc = self.lib.emu_simt_mc(self.model, C.byref(problem.c), seed, traj_id0, n_traj, n_steps, kind, ta, fs.ctypes.data, fsc.ctypes.data,
+                                  bs.ctypes.data, bsc.ctypes.data, bst.ctypes.data, oc.ctypes.data, 1 if fast else 0, threads,
+                                  self.POLICIES[policy], sched_seed, stats.ctypes.data)
+        if rc:
+            raise self._simt_err()
+        return [dict(final_seq=bytes(fs[k]).decode(), final_score=float(fsc[k]), best_seq=bytes(bs[k]).decode(), best_score=float(bsc[k]),
+                     best_step=int(bst[k]), outcomes=[int(v) for v in oc[k]]) for k in range(n_traj)]
+
+    def simt_selftest_missing_barrier(self, threads, policy, seed, with_barrier):
+        s = C.c_long()
+        self.lib.emu_simt_selftest_missing_barrier.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_long)]
+        if self.lib.emu_simt_selftest_missing_barrier(threads, self.POLICIES[policy], seed, 1 if with_barrier else 0, C.byref(s)):
+            raise self._simt_err()
+        return s.value
+
+    def simt_selftest_divergent_collective(self, threads, policy, seed):
+        self.lib.emu_simt_selftest_divergent_collective.argtypes = [C.c_int, C.c_int, C.c_uint64]
+        if self.lib.emu_simt_selftest_divergent_collective(threads, self.POLICIES[policy], seed):
+            raise self._simt_err()
+
+    def simt_drop_barrier(self, k):
+        """fault injection: every thread of the following simt_* runs returns from its k-th CTA barrier at once (-1: off)"""
+        self.lib.emu_simt_drop_barrier.argtypes = [C.c_long]
+        self.lib.emu_simt_drop_barrier(k)
