@@ -50,7 +50,7 @@
 
 namespace adp {
 
-// Phase timing for tuning (tools/variant_build.sh prof -DADP_PHASE_PROFILE, then tools/phase_run.py): every warp of CTA 0 accumulates clock64()
+// Phase timing for tuning (tools/variant_build.sh prof -DADP_PHASE_PROFILE, then tools/quick_time.py --phase): every warp of CTA 0 accumulates clock64()
 // deltas per phase of the column loop and prints them for the first jobs.  Off in the product build.
 #if defined(ADP_PHASE_PROFILE) && defined(__CUDACC__)
 static __device__ int g_prof_reports;
