@@ -53,3 +53,14 @@ def test_product_does_not_touch_the_oracle():
                 for line in text.splitlines():
                     if re.search(r"#include.*oracle|import\s+oracle|from\s+oracle|liboracle|orc_[a-z]+\(", line):
                         raise AssertionError("%s references the oracle: %s" % (os.path.join(dp, f), line.strip()))
+
+
+def test_header_is_plain_c_and_cxx11():
+    """the boundary is a C ABI: include/addapt_b200.h must compile as C99 (cgo / ctypes / JNI side) and as C++11 (the reference's
+    language level, configure.ac), with no torch or CUDA types in it"""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "addapt_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    includes = [ln for ln in open(hdr) if ln.lstrip().startswith("#include")]
+    assert all("<std" in ln for ln in includes), includes          # <stdint.h> / <stddef.h> only: no torch, no CUDA headers
